@@ -1,0 +1,554 @@
+// Whole-network launcher for the StyleGAN2 synthesis forward (reference networks.py:360-514) over
+// the fused kernels of this library.  Owns the packed weights, the style tables and the activation
+// workspace; forward() only enqueues kernels on the caller's stream.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "conv_common.cuh"
+
+namespace l2i {
+
+// kernels implemented in the other translation units
+template <typename T> int launch_conv_simt(const void*, const float*, const ConvGeom&, const EpiParams&, cudaStream_t);
+int launch_conv_tc(const void* in, const __nv_bfloat16* w, const ConvGeom& g, const EpiParams& e, cudaStream_t st);
+bool conv_tc_supported(const ConvGeom& g, const EpiParams& e);
+template <typename T>
+int launch_blur_act(void*, const void*, int, int, int, int, int, int, const float*, int64_t, const float*,
+                    const float*, const float*, int64_t, const float*, cudaStream_t);
+int launch_skip_combine(float*, const float*, int, const float*, const float*, int, int, int, const float*, cudaStream_t);
+template <typename T> int launch_const_input(void*, const float*, const float*, int64_t, int, int, int, cudaStream_t);
+int launch_demod(float*, int64_t, const float*, int64_t, const float*, const int64_t*, const int*, const int*, int, int, cudaStream_t);
+int launch_rgb_weight(float*, int64_t, const float*, const int*, const float*, int64_t, int, int, cudaStream_t);
+int launch_gather_latent(float*, const float*, int64_t, int64_t, int, int, int, cudaStream_t);
+int launch_pack_conv_weight(float*, __nv_bfloat16*, float*, const float*, int, int, int, float, cudaStream_t);
+int launch_scale_copy(float*, const float*, int64_t, float, cudaStream_t);
+template <typename T> int launch_nhwc_to_nchw(float*, const void*, int, int, int, int, const float*, int64_t, cudaStream_t);
+int launch_linear(float*, int64_t, const float*, int64_t, const int*, const float*, const float*, int, int, int,
+                  float, float, int, float, float, cudaStream_t);
+
+struct Param {
+  float* ptr = nullptr;
+  int64_t numel = 0;
+  bool set = false;
+};
+
+struct StyledConvLayer {
+  std::string name;  // "conv1" or "convs.j"
+  int cin, cout, res_in, res_out;
+  bool up;
+  int latent_idx, noise_idx;
+  int s_off;   // offset of this layer's styles inside a row of s_all
+  int d_off;   // offset of this layer's demod coefficients inside a row of d_all
+  float* w_f32 = nullptr;            // [9][Cin][Cout]
+  __nv_bfloat16* w_bf16 = nullptr;   // [9][Cout][Cin]
+  int64_t wsq_off = 0;
+};
+
+struct RgbLayer {
+  std::string name;  // "to_rgb1" or "to_rgbs.k"
+  int cin, res, latent_idx;
+  int s_off;    // inside s_all row
+  int wr_off;   // inside wr_all row
+};
+
+}  // namespace l2i
+
+using namespace l2i;
+
+struct l2i_generator {
+  int size, D, n_mlp, cm, dtype, max_batch, log_size, num_layers, n_latent;
+  float lr_mlp;
+  float fir[4];  // flipped separable taps * 2 (== taps / sum * 2)
+  bool finalized = false;
+  int last_batch = 0;
+  int conv_impl = 0;  // 0 auto, 1 simt, 2 tc
+
+  std::unordered_map<std::string, Param> params;
+  std::vector<StyledConvLayer> convs;
+  std::vector<RgbLayer> rgbs;
+
+  // style tables
+  int s_rows = 0, d_rows = 0, wr_elems = 0;
+  float *mod_w_all = nullptr, *mod_b_all = nullptr;
+  int* row_xoff = nullptr;
+  float* wsq_all = nullptr;
+  int64_t* row_wsq_off = nullptr;
+  int *row_s_off = nullptr, *row_cin = nullptr;
+  float* wrgb_all = nullptr;
+  int* rgb_elem_s_off = nullptr;
+
+  // workspace
+  float *latent_buf = nullptr, *s_all = nullptr, *d_all = nullptr, *wr_all = nullptr;
+  void* act[2] = {nullptr, nullptr};
+  void* tbuf = nullptr;
+  float* rgb_part = nullptr;
+  float* skip[2] = {nullptr, nullptr};
+  float* map_buf[2] = {nullptr, nullptr};
+  // where each layer's output landed in the last forward (debug taps)
+  std::vector<const void*> conv_out;
+  std::vector<const float*> skip_out;
+
+  std::vector<void*> allocs;
+  size_t elem_size() const { return dtype == L2I_F32 ? 4 : 2; }
+};
+
+namespace {
+
+int channels_at(int res, int cm) {
+  switch (res) {
+    case 4: case 8: case 16: case 32: return 512;
+    case 64: return 256 * cm;
+    case 128: return 128 * cm;
+    case 256: return 64 * cm;
+    case 512: return 32 * cm;
+    case 1024: return 16 * cm;
+    default: return -1;
+  }
+}
+
+template <typename T>
+int dev_alloc(l2i_generator* g, T** p, int64_t n) {
+  *p = nullptr;
+  if (n <= 0) return L2I_OK;
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, (size_t)n * sizeof(T));
+  if (e != cudaSuccess) {
+    set_error("generator: cudaMalloc(%lld bytes) failed: %s", (long long)(n * (int64_t)sizeof(T)), cudaGetErrorString(e));
+    return L2I_ERR_CUDA;
+  }
+  g->allocs.push_back(q);
+  *p = (T*)q;
+  return L2I_OK;
+}
+
+int add_param(l2i_generator* g, const std::string& key, int64_t numel) {
+  Param p;
+  p.numel = numel;
+  L2I_TRY(dev_alloc(g, &p.ptr, numel));
+  g->params[key] = p;
+  return L2I_OK;
+}
+
+float* P(l2i_generator* g, const std::string& key) { return g->params.at(key).ptr; }
+
+TapList plain_taps() {
+  TapList t{};
+  t.n = 9;
+  for (int kh = 0; kh < 3; ++kh)
+    for (int kw = 0; kw < 3; ++kw) {
+      int i = kh * 3 + kw;
+      t.dy[i] = (int8_t)(kh - 1);
+      t.dx[i] = (int8_t)(kw - 1);
+      t.wtap[i] = (int8_t)i;
+    }
+  return t;
+}
+
+// stride-2 transposed 3x3 conv, output phase (py, px): t[2*oy+py, 2*ox+px] gathers the taps kh = py
+// (mod 2) from input row oy - kh/2 (conv_transpose2d: u = 2*y + kh), same for columns.
+TapList upconv_taps(int py, int px) {
+  TapList t{};
+  t.n = 0;
+  for (int kh = py; kh < 3; kh += 2)
+    for (int kw = px; kw < 3; kw += 2) {
+      t.dy[t.n] = (int8_t)(-(kh / 2));
+      t.dx[t.n] = (int8_t)(-(kw / 2));
+      t.wtap[t.n] = (int8_t)(kh * 3 + kw);
+      ++t.n;
+    }
+  return t;
+}
+
+int run_conv(l2i_generator* g, const StyledConvLayer& L, const void* in, const ConvGeom& geom, const EpiParams& e,
+             cudaStream_t st) {
+  if (g->dtype == L2I_F32) return launch_conv_simt<float>(in, L.w_f32, geom, e, st);
+  const bool want_tc = g->conv_impl != 1;
+  if (want_tc && conv_tc_supported(geom, e)) return launch_conv_tc(in, L.w_bf16, geom, e, st);
+  if (g->conv_impl == 2) {
+    set_error("generator: L2I_CONV_IMPL=tc but layer %s is not supported by the tcgen05 kernel", L.name.c_str());
+    return L2I_ERR_UNSUPPORTED;
+  }
+  return launch_conv_simt<__nv_bfloat16>(in, L.w_f32, geom, e, st);
+}
+
+}  // namespace
+
+extern "C" int l2i_generator_create(l2i_generator_t** out, int size, int style_dim, int n_mlp, int channel_multiplier,
+                                    const float* blur_taps, int n_blur_taps, float lr_mlp, int dtype, int max_batch) {
+  L2I_REQUIRE(out != nullptr, "generator_create: null out");
+  *out = nullptr;
+  L2I_REQUIRE(size >= 8 && size <= 1024 && (size & (size - 1)) == 0, "generator_create: size %d must be a power of two in 8..1024", size);
+  L2I_REQUIRE(style_dim >= 1 && n_mlp >= 0 && channel_multiplier >= 1, "generator_create: bad style_dim/n_mlp/channel_multiplier");
+  L2I_REQUIRE(dtype == L2I_F32 || dtype == L2I_BF16, "generator_create: dtype must be L2I_F32 or L2I_BF16");
+  L2I_REQUIRE(max_batch >= 1, "generator_create: max_batch must be >= 1");
+  L2I_REQUIRE(blur_taps != nullptr && n_blur_taps == 4,
+              "generator_create: the fused up-conv/blur path needs a 4-tap separable blur kernel (got %d taps)", n_blur_taps);
+
+  l2i_generator* g = new l2i_generator();
+  g->size = size; g->D = style_dim; g->n_mlp = n_mlp; g->cm = channel_multiplier; g->dtype = dtype;
+  g->max_batch = max_batch; g->lr_mlp = lr_mlp;
+  g->log_size = (int)std::lround(std::log2((double)size));
+  g->num_layers = (g->log_size - 2) * 2 + 1;
+  g->n_latent = g->log_size * 2 - 2;
+  {
+    float sum = 0.f;
+    for (int i = 0; i < 4; ++i) sum += blur_taps[i];
+    // make_kernel(k) * factor^2 == outer(f, f) with f = taps / sum * 2; upfirdn2d correlates with the flip
+    for (int i = 0; i < 4; ++i) g->fir[i] = blur_taps[3 - i] / sum * 2.f;
+  }
+  if (const char* env = std::getenv("L2I_CONV_IMPL")) {
+    if (!std::strcmp(env, "simt")) g->conv_impl = 1;
+    else if (!std::strcmp(env, "tc")) g->conv_impl = 2;
+  }
+
+  int rc = L2I_OK;
+  auto fail = [&](int code) { l2i_generator_destroy(g); return code; };
+  const int D = style_dim;
+
+  // ---- layer table (networks.py:396-438) ----
+  {
+    StyledConvLayer c1;
+    c1.name = "conv1"; c1.cin = c1.cout = channels_at(4, g->cm); c1.res_in = c1.res_out = 4; c1.up = false;
+    c1.latent_idx = 0; c1.noise_idx = 0;
+    g->convs.push_back(c1);
+    RgbLayer r1;
+    r1.name = "to_rgb1"; r1.cin = c1.cout; r1.res = 4; r1.latent_idx = 1;
+    g->rgbs.push_back(r1);
+    int cin = c1.cout;
+    for (int k = 0; k < g->log_size - 2; ++k) {
+      const int res_in = 4 << k, res_out = res_in * 2;
+      const int cout = channels_at(res_out, g->cm);
+      StyledConvLayer up;
+      up.name = "convs." + std::to_string(2 * k); up.cin = cin; up.cout = cout; up.res_in = res_in; up.res_out = res_out;
+      up.up = true; up.latent_idx = 2 * k + 1; up.noise_idx = 2 * k + 1;
+      g->convs.push_back(up);
+      StyledConvLayer cv;
+      cv.name = "convs." + std::to_string(2 * k + 1); cv.cin = cout; cv.cout = cout; cv.res_in = cv.res_out = res_out;
+      cv.up = false; cv.latent_idx = 2 * k + 2; cv.noise_idx = 2 * k + 2;
+      g->convs.push_back(cv);
+      RgbLayer r;
+      r.name = "to_rgbs." + std::to_string(k); r.cin = cout; r.res = res_out; r.latent_idx = 2 * k + 3;
+      g->rgbs.push_back(r);
+      cin = cout;
+    }
+  }
+
+  // ---- parameter slots (rosinality state_dict keys) ----
+  for (int i = 1; i <= n_mlp && rc == L2I_OK; ++i) {
+    rc = add_param(g, "style." + std::to_string(i) + ".weight", (int64_t)D * D);
+    if (rc == L2I_OK) rc = add_param(g, "style." + std::to_string(i) + ".bias", D);
+  }
+  if (rc == L2I_OK) rc = add_param(g, "input.input", (int64_t)g->convs[0].cin * 16);
+  for (auto& L : g->convs) {
+    if (rc != L2I_OK) break;
+    rc = add_param(g, L.name + ".conv.weight", (int64_t)L.cout * L.cin * 9);
+    if (rc == L2I_OK) rc = add_param(g, L.name + ".conv.modulation.weight", (int64_t)L.cin * D);
+    if (rc == L2I_OK) rc = add_param(g, L.name + ".conv.modulation.bias", L.cin);
+    if (rc == L2I_OK) rc = add_param(g, L.name + ".noise.weight", 1);
+    if (rc == L2I_OK) rc = add_param(g, L.name + ".activate.bias", L.cout);
+  }
+  for (auto& R : g->rgbs) {
+    if (rc != L2I_OK) break;
+    rc = add_param(g, R.name + ".bias", 3);
+    if (rc == L2I_OK) rc = add_param(g, R.name + ".conv.weight", (int64_t)3 * R.cin);
+    if (rc == L2I_OK) rc = add_param(g, R.name + ".conv.modulation.weight", (int64_t)R.cin * D);
+    if (rc == L2I_OK) rc = add_param(g, R.name + ".conv.modulation.bias", R.cin);
+  }
+  if (rc != L2I_OK) return fail(rc);
+
+  // ---- style / demod / rgb tables ----
+  int s_rows = 0, d_rows = 0, wr_elems = 0;
+  int64_t wsq_total = 0;
+  for (auto& L : g->convs) { L.s_off = s_rows; s_rows += L.cin; L.d_off = d_rows; d_rows += L.cout; L.wsq_off = wsq_total; wsq_total += (int64_t)L.cout * L.cin; }
+  for (auto& R : g->rgbs) { R.s_off = s_rows; s_rows += R.cin; R.wr_off = wr_elems; wr_elems += 3 * R.cin; }
+  g->s_rows = s_rows; g->d_rows = d_rows; g->wr_elems = wr_elems;
+  rc = dev_alloc(g, &g->mod_w_all, (int64_t)s_rows * D);
+  if (rc == L2I_OK) rc = dev_alloc(g, &g->mod_b_all, s_rows);
+  if (rc == L2I_OK) rc = dev_alloc(g, &g->row_xoff, s_rows);
+  if (rc == L2I_OK) rc = dev_alloc(g, &g->wsq_all, wsq_total);
+  if (rc == L2I_OK) rc = dev_alloc(g, &g->row_wsq_off, d_rows);
+  if (rc == L2I_OK) rc = dev_alloc(g, &g->row_s_off, d_rows);
+  if (rc == L2I_OK) rc = dev_alloc(g, &g->row_cin, d_rows);
+  if (rc == L2I_OK) rc = dev_alloc(g, &g->wrgb_all, wr_elems);
+  if (rc == L2I_OK) rc = dev_alloc(g, &g->rgb_elem_s_off, wr_elems);
+  if (rc != L2I_OK) return fail(rc);
+  {
+    std::vector<int> xoff(s_rows), rs(d_rows), rc_(d_rows), eoff(wr_elems);
+    std::vector<int64_t> rw(d_rows);
+    for (auto& L : g->convs) {
+      for (int i = 0; i < L.cin; ++i) xoff[L.s_off + i] = L.latent_idx * D;
+      for (int co = 0; co < L.cout; ++co) {
+        rw[L.d_off + co] = L.wsq_off + (int64_t)co * L.cin;
+        rs[L.d_off + co] = L.s_off;
+        rc_[L.d_off + co] = L.cin;
+      }
+    }
+    for (auto& R : g->rgbs) {
+      for (int i = 0; i < R.cin; ++i) xoff[R.s_off + i] = R.latent_idx * D;
+      for (int c = 0; c < 3; ++c)
+        for (int i = 0; i < R.cin; ++i) eoff[R.wr_off + c * R.cin + i] = R.s_off + i;
+    }
+    cudaError_t e = cudaMemcpy(g->row_xoff, xoff.data(), sizeof(int) * s_rows, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(g->row_wsq_off, rw.data(), sizeof(int64_t) * d_rows, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(g->row_s_off, rs.data(), sizeof(int) * d_rows, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(g->row_cin, rc_.data(), sizeof(int) * d_rows, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(g->rgb_elem_s_off, eoff.data(), sizeof(int) * wr_elems, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { set_error("generator_create: table upload failed: %s", cudaGetErrorString(e)); return fail(L2I_ERR_CUDA); }
+  }
+
+  // ---- packed weights ----
+  for (auto& L : g->convs) {
+    rc = dev_alloc(g, &L.w_f32, (int64_t)9 * L.cin * L.cout);
+    if (rc == L2I_OK && dtype == L2I_BF16) rc = dev_alloc(g, &L.w_bf16, (int64_t)9 * L.cin * L.cout);
+    if (rc != L2I_OK) return fail(rc);
+  }
+
+  // ---- workspace ----
+  const int64_t B = max_batch;
+  int64_t act_elems = 0, t_elems = 0, part_elems = 0;
+  for (auto& L : g->convs) {
+    act_elems = std::max(act_elems, B * L.res_out * L.res_out * (int64_t)L.cout);
+    act_elems = std::max(act_elems, B * L.res_in * L.res_in * (int64_t)L.cin);
+    if (L.up) t_elems = std::max(t_elems, B * (int64_t)(2 * L.res_in + 2) * (2 * L.res_in + 2) * L.cout);
+  }
+  for (auto& R : g->rgbs) part_elems = std::max(part_elems, B * 3 * (int64_t)R.res * R.res * ceil_div(R.cin, 64));
+  const size_t es = g->elem_size();
+  {
+    char *a0 = nullptr, *a1 = nullptr, *tb = nullptr;
+    rc = dev_alloc(g, &a0, act_elems * (int64_t)es);
+    if (rc == L2I_OK) rc = dev_alloc(g, &a1, act_elems * (int64_t)es);
+    if (rc == L2I_OK) rc = dev_alloc(g, &tb, t_elems * (int64_t)es);
+    g->act[0] = a0; g->act[1] = a1; g->tbuf = tb;
+  }
+  if (rc == L2I_OK) rc = dev_alloc(g, &g->rgb_part, part_elems);
+  if (rc == L2I_OK) rc = dev_alloc(g, &g->skip[0], B * 3 * (int64_t)size * size);
+  if (rc == L2I_OK) rc = dev_alloc(g, &g->skip[1], B * 3 * (int64_t)(size / 2) * (size / 2));
+  if (rc == L2I_OK) rc = dev_alloc(g, &g->latent_buf, B * g->n_latent * (int64_t)D);
+  if (rc == L2I_OK) rc = dev_alloc(g, &g->s_all, B * (int64_t)s_rows);
+  if (rc == L2I_OK) rc = dev_alloc(g, &g->d_all, B * (int64_t)d_rows);
+  if (rc == L2I_OK) rc = dev_alloc(g, &g->wr_all, B * (int64_t)wr_elems);
+  if (rc == L2I_OK) rc = dev_alloc(g, &g->map_buf[0], B * (int64_t)D);
+  if (rc == L2I_OK) rc = dev_alloc(g, &g->map_buf[1], B * (int64_t)D);
+  if (rc != L2I_OK) return fail(rc);
+  g->conv_out.assign(g->convs.size(), nullptr);
+  g->skip_out.assign(g->rgbs.size(), nullptr);
+  *out = g;
+  return L2I_OK;
+}
+
+extern "C" void l2i_generator_destroy(l2i_generator_t* g) {
+  if (!g) return;
+  for (void* p : g->allocs) cudaFree(p);
+  delete g;
+}
+
+extern "C" int l2i_generator_num_layers(const l2i_generator_t* g) { return g ? g->num_layers : -1; }
+extern "C" int l2i_generator_n_latent(const l2i_generator_t* g) { return g ? g->n_latent : -1; }
+
+extern "C" int l2i_generator_set_param(l2i_generator_t* g, const char* key, const float* data, int64_t numel, void* stream) {
+  L2I_REQUIRE(g && key, "generator_set_param: null argument");
+  const std::string k(key);
+  // buffers the native side does not consume: FIR kernels are fixed at create time, the registered
+  // noise buffers are passed explicitly to forward()
+  if (k.find(".blur.kernel") != std::string::npos || k.find(".upsample.kernel") != std::string::npos ||
+      k.rfind("noises.", 0) == 0)
+    return L2I_OK;
+  auto it = g->params.find(k);
+  L2I_REQUIRE(it != g->params.end(), "generator_set_param: unknown key '%s'", key);
+  L2I_REQUIRE(it->second.numel == numel, "generator_set_param: '%s' expects %lld elements, got %lld", key,
+              (long long)it->second.numel, (long long)numel);
+  L2I_REQUIRE(data != nullptr, "generator_set_param: null data for '%s'", key);
+  L2I_CUDA_TRY(cudaMemcpyAsync(it->second.ptr, data, sizeof(float) * numel, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  it->second.set = true;
+  g->finalized = false;
+  return L2I_OK;
+}
+
+extern "C" int l2i_generator_finalize(l2i_generator_t* g, void* stream) {
+  L2I_REQUIRE(g, "generator_finalize: null generator");
+  for (auto& kv : g->params)
+    if (!kv.second.set) {
+      set_error("generator_finalize: parameter '%s' was never set", kv.first.c_str());
+      return L2I_ERR_STATE;
+    }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = g->D;
+  const float mod_scale = 1.0f / std::sqrt((float)D);  // EqualLinear(style_dim, Cin, bias_init=1): lr_mul = 1
+  for (auto& L : g->convs) {
+    const float scale = 1.0f / std::sqrt((float)(L.cin * 9));
+    L2I_TRY(launch_pack_conv_weight(L.w_f32, L.w_bf16, g->wsq_all + L.wsq_off, P(g, L.name + ".conv.weight"), L.cout,
+                                    L.cin, 9, scale, st));
+    L2I_TRY(launch_scale_copy(g->mod_w_all + (int64_t)L.s_off * D, P(g, L.name + ".conv.modulation.weight"),
+                              (int64_t)L.cin * D, mod_scale, st));
+    L2I_TRY(launch_scale_copy(g->mod_b_all + L.s_off, P(g, L.name + ".conv.modulation.bias"), L.cin, 1.f, st));
+  }
+  for (auto& R : g->rgbs) {
+    const float scale = 1.0f / std::sqrt((float)R.cin);
+    L2I_TRY(launch_scale_copy(g->wrgb_all + R.wr_off, P(g, R.name + ".conv.weight"), (int64_t)3 * R.cin, scale, st));
+    L2I_TRY(launch_scale_copy(g->mod_w_all + (int64_t)R.s_off * D, P(g, R.name + ".conv.modulation.weight"),
+                              (int64_t)R.cin * D, mod_scale, st));
+    L2I_TRY(launch_scale_copy(g->mod_b_all + R.s_off, P(g, R.name + ".conv.modulation.bias"), R.cin, 1.f, st));
+  }
+  g->finalized = true;
+  return L2I_OK;
+}
+
+extern "C" int l2i_generator_mapping(l2i_generator_t* g, float* w, const float* z, int batch, void* stream) {
+  L2I_REQUIRE(g && (batch == 0 || (w && z)), "generator_mapping: null argument");
+  if (!g->finalized) { set_error("generator_mapping: call l2i_generator_finalize first"); return L2I_ERR_STATE; }
+  if (batch > g->max_batch) { set_error("generator_mapping: batch %d > max_batch %d", batch, g->max_batch); return L2I_ERR_STATE; }
+  if (batch == 0) return L2I_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = g->D;
+  float* cur = g->n_mlp == 0 ? w : g->map_buf[0];
+  L2I_TRY(l2i_pixel_norm(cur, z, batch, D, stream));
+  const float wscale = (1.0f / std::sqrt((float)D)) * g->lr_mlp;
+  for (int i = 1; i <= g->n_mlp; ++i) {
+    float* nxt = (i == g->n_mlp) ? w : g->map_buf[i & 1];
+    L2I_TRY(launch_linear(nxt, D, cur, D, nullptr, P(g, "style." + std::to_string(i) + ".weight"),
+                          P(g, "style." + std::to_string(i) + ".bias"), batch, D, D, wscale, g->lr_mlp, 1, 0.2f,
+                          1.4142135623730951f, st));
+    cur = nxt;
+  }
+  return L2I_OK;
+}
+
+extern "C" int l2i_generator_forward(l2i_generator_t* g, const float* latent, int64_t latent_batch_stride,
+                                     int64_t latent_layer_stride, const float* const* noise, const int* noise_batch,
+                                     float* image, uint8_t* image_u8, int batch, void* stream) {
+  L2I_REQUIRE(g, "generator_forward: null generator");
+  if (!g->finalized) { set_error("generator_forward: call l2i_generator_finalize first"); return L2I_ERR_STATE; }
+  if (batch > g->max_batch) { set_error("generator_forward: batch %d > max_batch %d", batch, g->max_batch); return L2I_ERR_STATE; }
+  L2I_REQUIRE(batch >= 0, "generator_forward: negative batch");
+  if (batch == 0) return L2I_OK;
+  L2I_REQUIRE(latent != nullptr, "generator_forward: null latent");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = batch, D = g->D;
+  const bool f32 = g->dtype == L2I_F32;
+  for (int i = 0; i < g->num_layers; ++i)
+    if (noise != nullptr && noise[i] != nullptr)
+      L2I_REQUIRE(noise_batch != nullptr && (noise_batch[i] == 1 || noise_batch[i] == B),
+                  "generator_forward: noise[%d] batch must be 1 or %d", i, B);
+
+  // 1. styles for every modulated conv, demodulation coefficients, ToRGB effective weights
+  L2I_TRY(launch_gather_latent(g->latent_buf, latent, latent_batch_stride, latent_layer_stride, B, g->n_latent, D, st));
+  L2I_TRY(launch_linear(g->s_all, g->s_rows, g->latent_buf, (int64_t)g->n_latent * D, g->row_xoff, g->mod_w_all,
+                        g->mod_b_all, B, g->s_rows, D, 1.f, 1.f, 0, 0.f, 1.f, st));
+  L2I_TRY(launch_demod(g->d_all, g->d_rows, g->s_all, g->s_rows, g->wsq_all, g->row_wsq_off, g->row_s_off, g->row_cin,
+                       g->d_rows, B, st));
+  L2I_TRY(launch_rgb_weight(g->wr_all, g->wr_elems, g->wrgb_all, g->rgb_elem_s_off, g->s_all, g->s_rows, g->wr_elems, B, st));
+
+  // 2. constant input scaled by conv1's style
+  int cur = 0;
+  {
+    const auto& L = g->convs[0];
+    if (f32) L2I_TRY(launch_const_input<float>(g->act[cur], P(g, "input.input"), g->s_all + L.s_off, g->s_rows, B, L.cin, 16, st));
+    else L2I_TRY(launch_const_input<__nv_bfloat16>(g->act[cur], P(g, "input.input"), g->s_all + L.s_off, g->s_rows, B, L.cin, 16, st));
+  }
+
+  // 3. layers
+  const float* skip_prev = nullptr;
+  int skip_sel = (int)(g->rgbs.size() - 1) & 1;  // arrange that the final skip lands in skip[0] (full-size buffer)
+  size_t rgb_i = 0;
+  for (size_t li = 0; li < g->convs.size(); ++li) {
+    const auto& L = g->convs[li];
+    const bool last_conv = li + 1 == g->convs.size();
+    const StyledConvLayer* next = last_conv ? nullptr : &g->convs[li + 1];
+    const float* nz = noise ? noise[L.noise_idx] : nullptr;
+    const int64_t nz_bs = (nz && noise_batch[L.noise_idx] == B && B > 1) ? (int64_t)L.res_out * L.res_out : 0;
+    const float* nz_w = P(g, L.name + ".noise.weight");
+    const float* s_next = next ? g->s_all + next->s_off : nullptr;
+
+    ConvGeom geom{};
+    geom.B = B; geom.H = geom.W = L.res_in; geom.Cin = L.cin; geom.Cout = L.cout;
+    EpiParams e{};
+    e.demod = g->d_all + L.d_off; e.demod_bs = g->d_rows;
+    for (int i = 0; i < 4; ++i) e.fir[i] = g->fir[i];
+
+    if (L.up) {
+      geom.OH = geom.OW = L.res_in + 1; geom.nphase = 4; geom.out_scale = 2;
+      geom.out_H = geom.out_W = 2 * L.res_in + 2;
+      for (int ph = 0; ph < 4; ++ph) geom.taps[ph] = upconv_taps(ph >> 1, ph & 1);
+      e.mode = 1; e.out = g->tbuf;
+      L2I_TRY(run_conv(g, L, g->act[cur], geom, e, st));
+      void* dst = g->act[cur ^ 1];
+      if (f32) L2I_TRY(launch_blur_act<float>(dst, g->tbuf, B, L.res_out, L.res_out, L.cout, geom.out_H, geom.out_W, nz, nz_bs, nz_w,
+                                              P(g, L.name + ".activate.bias"), s_next, g->s_rows, g->fir, st));
+      else L2I_TRY(launch_blur_act<__nv_bfloat16>(dst, g->tbuf, B, L.res_out, L.res_out, L.cout, geom.out_H, geom.out_W, nz, nz_bs,
+                                                  nz_w, P(g, L.name + ".activate.bias"), s_next, g->s_rows, g->fir, st));
+      cur ^= 1;
+      g->conv_out[li] = g->act[cur];
+      continue;
+    }
+
+    // plain styled conv, followed by a ToRGB (conv1 -> to_rgb1, convs[odd] -> to_rgbs[k])
+    const auto& R = g->rgbs[rgb_i];
+    geom.OH = geom.OW = L.res_in; geom.nphase = 1; geom.out_scale = 1; geom.out_H = geom.out_W = L.res_out;
+    geom.taps[0] = plain_taps();
+    e.mode = 0;
+    e.bias = P(g, L.name + ".activate.bias");
+    e.noise = nz; e.noise_bs = nz_bs; e.noise_w = nz_w;
+    e.s_next = s_next; e.s_next_bs = g->s_rows;
+    e.out = s_next ? g->act[cur ^ 1] : nullptr;
+    e.wr = g->wr_all + R.wr_off; e.wr_bs = g->wr_elems;
+    e.rgb_bias = P(g, R.name + ".bias");
+    e.skip_in = skip_prev;
+    const bool final_rgb = rgb_i + 1 == g->rgbs.size();
+    float* skip_dst = (final_rgb && image != nullptr) ? image : g->skip[skip_sel];
+    e.skip_out = skip_dst;
+    e.rgb_part = g->rgb_part;
+    const int n_tile = (f32 || g->conv_impl == 1 || !conv_tc_supported(geom, e)) ? 64 : 256;
+    const int nparts = ceil_div(L.cout, n_tile);
+    e.fused_skip = nparts == 1 ? 1 : 0;
+    L2I_TRY(run_conv(g, L, g->act[cur], geom, e, st));
+    if (!e.fused_skip)
+      L2I_TRY(launch_skip_combine(skip_dst, g->rgb_part, nparts, e.rgb_bias, skip_prev, B, L.res_out, L.res_out, g->fir, st));
+    if (s_next) cur ^= 1;
+    g->conv_out[li] = s_next ? g->act[cur] : nullptr;
+    g->skip_out[rgb_i] = skip_dst;
+    skip_prev = skip_dst;
+    skip_sel ^= 1;
+    ++rgb_i;
+  }
+  if (image_u8 != nullptr) L2I_TRY(l2i_image_to_uint8(image_u8, skip_prev, B, g->size, g->size, stream));
+  g->last_batch = B;
+  return L2I_OK;
+}
+
+extern "C" int l2i_generator_backward(l2i_generator_t* g, float* grad_latent, const float* grad_image, int batch, void* stream) {
+  (void)g; (void)grad_latent; (void)grad_image; (void)batch; (void)stream;
+  set_error("generator_backward: not implemented in this build");
+  return L2I_ERR_UNSUPPORTED;
+}
+
+extern "C" int l2i_generator_read_activation(l2i_generator_t* g, const char* name, float* out, int64_t numel, int batch,
+                                             void* stream) {
+  L2I_REQUIRE(g && name && out, "generator_read_activation: null argument");
+  if (batch != g->last_batch) { set_error("generator_read_activation: batch %d does not match the last forward (%d)", batch, g->last_batch); return L2I_ERR_STATE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const std::string n(name);
+  if (n.rfind("skip.", 0) == 0) {
+    const int k = std::atoi(n.c_str() + 5);
+    L2I_REQUIRE(k >= 0 && k < (int)g->rgbs.size() && g->skip_out[k] != nullptr, "generator_read_activation: no such skip '%s'", name);
+    const int64_t need = (int64_t)batch * 3 * g->rgbs[k].res * g->rgbs[k].res;
+    L2I_REQUIRE(numel == need, "generator_read_activation: '%s' has %lld elements", name, (long long)need);
+    L2I_CUDA_TRY(cudaMemcpyAsync(out, g->skip_out[k], sizeof(float) * need, cudaMemcpyDeviceToDevice, st));
+    return L2I_OK;
+  }
+  for (size_t li = 0; li < g->convs.size(); ++li) {
+    const auto& L = g->convs[li];
+    if (L.name != n) continue;
+    L2I_REQUIRE(g->conv_out[li] != nullptr && li + 1 < g->convs.size(), "generator_read_activation: '%s' is not materialised", name);
+    const int64_t need = (int64_t)batch * L.cout * L.res_out * L.res_out;
+    L2I_REQUIRE(numel == need, "generator_read_activation: '%s' has %lld elements", name, (long long)need);
+    const float* inv = g->s_all + g->convs[li + 1].s_off;
+    if (g->dtype == L2I_F32) return launch_nhwc_to_nchw<float>(out, g->conv_out[li], batch, L.res_out, L.res_out, L.cout, inv, g->s_rows, st);
+    return launch_nhwc_to_nchw<__nv_bfloat16>(out, g->conv_out[li], batch, L.res_out, L.res_out, L.cout, inv, g->s_rows, st);
+  }
+  set_error("generator_read_activation: unknown activation '%s'", name);
+  return L2I_ERR_INVALID_ARG;
+}

@@ -1,0 +1,22 @@
+"""Run-time configuration of the StyleGAN2 graph (reference constants.py:1-25, made configurable).
+
+The reference hard-codes 256 px / batch 4; here every value can be overridden through the
+environment (``L2I_RESOLUTION``, ``L2I_BATCH_SIZE``, ``L2I_DTYPE``, ``L2I_G_PATH``, ``L2I_REG_PATH``)
+or by assigning to this module before the graph is built.
+"""
+import os
+
+BATCH_SIZE = int(os.environ.get("L2I_BATCH_SIZE", 4))
+DIM_Z = 512
+resolution = int(os.environ.get("L2I_RESOLUTION", 256))
+useGPU = True
+NUM_CHANNELS = 3
+
+# checkpoints: rosinality-format generator ({'g_ema': state_dict}) and ResNet-50 regressor ({'model': ...})
+reg_json = None
+reg_path = os.environ.get("L2I_REG_PATH", "/path/003_dict.model")
+g_path = os.environ.get("L2I_G_PATH", "/path/550000.pt")
+# with no checkpoint on disk the modules keep their random initialisation (benchmarks, tests)
+allow_random_init = True
+compute_dtype = "fp32" if os.environ.get("L2I_DTYPE", "bf16").lower() in ("fp32", "f32", "float32") else "bf16"
+walk_is_mlp = False

@@ -1,0 +1,428 @@
+"""Walk modules and the TransformGraph orchestrator over the native hot path.
+
+Drop-in for ``graphs/stylegan_v2_real/transform_base.py`` of KelestZ/Latent2im: the three W-space
+walk modules on the path (``WalkLinearMultiW`` :140-165, ``WalkMlpMultiW`` :168-204,
+``WalkNonLinearW`` :207-243) keep their class names, constructor signatures and parameter names
+(``w``, ``linear.{0,2,4}.*``, ``embed.*``) so whole-module pickles written by the reference load;
+``TransformGraph`` keeps the method set the entry scripts call.
+The walk step runs in ``l2i_walk_linear_fwd`` / ``l2i_walk_combine`` + ``l2i_linear_fwd``; the
+walk-parameter gradient in ``l2i_walk_linear_bwd``.
+
+Deviations from the shipped reference, all documented in DESIGN.md:
+* size / batch / dtype come from ``constants`` instead of being hard-coded to 256 px, batch 4;
+* ``WalkMlpMultiW`` with ``layers=...`` applies the same MLP to the chosen layers (the reference
+  calls ``self.linear(input[i], 1)``, a TypeError); ``WalkNonLinearW`` accepts the keyword call
+  ``walk(ws, alpha=..., layers=...)`` that ``get_w_new_tensor`` makes (TypeError as shipped);
+* G-forward #1 / R-forward #1 of the training step run without autograd (the branch contributes
+  exactly zero to the walk gradient);
+* the discriminator and VGG19 loss terms are only built when their loss is requested.
+"""
+import os
+
+import numpy as np
+import torch
+from torch import nn
+from torch.autograd import Function
+
+from latent2im_b200 import _native as nt
+
+from . import constants
+
+
+# ------------------------------------------------------------------------------------------------
+# native walk steps as autograd Functions
+# ------------------------------------------------------------------------------------------------
+def _as_latent_block(ws):
+    """list of n_latent [B, D] tensors -> (tensor, batch_stride, layer_stride).  The W+ list built
+    by get_w is one tensor repeated (transform_base.py:372-378): no copy, layer stride 0."""
+    first = ws[0]
+    nt.require_cuda(first, "input")
+    if all(w is first for w in ws):
+        base = first.detach().float().contiguous()
+        return base, base.stride(0), 0
+    blk = torch.stack([w.detach().float() for w in ws], 1).contiguous()
+    return blk, blk.stride(0), blk.stride(1)
+
+
+def _layer_mask(n, layers):
+    if layers is None:
+        return (1 << n) - 1
+    m = 0
+    for i in layers:
+        i = int(i)
+        if 0 <= i < n:
+            m |= 1 << i
+    return m
+
+
+class _WalkLinearFn(Function):
+    @staticmethod
+    def forward(ctx, w_param, alpha, mask, n_latent, *ws):
+        blk, bs, ls = _as_latent_block(ws)
+        B, D = ws[0].shape
+        al = alpha.detach().float().contiguous()
+        wp = w_param.detach().float().contiguous()
+        out = torch.empty(B, n_latent, D, device=blk.device, dtype=torch.float32)
+        with torch.cuda.device(blk.device):
+            nt.check(nt.load().l2i_walk_linear_fwd(out.data_ptr(), blk.data_ptr(), bs, ls, nt.ptr(al), nt.ptr(wp), B,
+                                                   al.shape[1], n_latent, D, mask, nt.stream_ptr(blk.device)),
+                     "walk_linear_fwd")
+        ctx.save_for_backward(al)
+        ctx.cfg = (mask, n_latent, D, wp.shape[0], len(ws), all(w is ws[0] for w in ws))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (al,) = ctx.saved_tensors
+        mask, n_latent, D, A, n_in, shared = ctx.cfg
+        g = grad_out.contiguous().float()
+        gw = torch.empty(A, n_latent, D, device=g.device, dtype=torch.float32)
+        with torch.cuda.device(g.device):
+            nt.check(nt.load().l2i_walk_linear_bwd(gw.data_ptr(), g.data_ptr(), al.data_ptr(), g.shape[0], A, n_latent, D,
+                                                   mask, nt.stream_ptr(g.device)), "walk_linear_bwd")
+        # d out_i / d in_i = I; d out / d alpha is never needed on the training path (epsilon is a value)
+        gins = tuple(g[:, i] for i in range(n_in))
+        return (gw, None, None, None) + gins
+
+
+class _LinearFn(Function):
+    """y = act(x W^T + b) through l2i_linear_fwd; backward reuses the same kernel on transposed operands."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, act):
+        nt.require_cuda(x, "input")
+        x2 = x.detach().float().contiguous()
+        Wc, bc = W.detach().float().contiguous(), b.detach().float().contiguous()
+        B, K = x2.shape
+        N = Wc.shape[0]
+        y = torch.empty(B, N, device=x2.device, dtype=torch.float32)
+        with torch.cuda.device(x2.device):
+            nt.check(nt.load().l2i_linear_fwd(y.data_ptr(), N, x2.data_ptr(), K, Wc.data_ptr(), bc.data_ptr(), B, N, K, 1.0, 1.0,
+                                              1 if act else 0, 0.2, 1.0, nt.stream_ptr(x2.device)), "linear_fwd")
+        ctx.save_for_backward(x2, Wc, y)
+        ctx.act = act
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, Wc, y = ctx.saved_tensors
+        lib = nt.load()
+        g = gy.contiguous().float()
+        B, K = x2.shape
+        N = Wc.shape[0]
+        dev = g.device
+        with torch.cuda.device(dev):
+            st = nt.stream_ptr(dev)
+            if ctx.act:  # leaky relu derivative from the saved output's sign
+                g2 = torch.empty_like(g)
+                nt.check(lib.l2i_fused_bias_act(g2.data_ptr(), g.data_ptr(), None, y.data_ptr(), g.numel(), 1, 0, 3, 1, 0.2, 1.0,
+                                                nt.F32, st), "fused_bias_act")
+                g = g2
+            gx = torch.empty(B, K, device=dev, dtype=torch.float32)
+            Wt = Wc.t().contiguous()
+            nt.check(lib.l2i_linear_fwd(gx.data_ptr(), K, g.data_ptr(), N, Wt.data_ptr(), None, B, K, N, 1.0, 0.0, 0, 0.0, 1.0, st),
+                     "linear_bwd_x")
+            gW = torch.empty(N, K, device=dev, dtype=torch.float32)
+            gt, xt = g.t().contiguous(), x2.t().contiguous()
+            nt.check(lib.l2i_linear_fwd(gW.data_ptr(), K, gt.data_ptr(), B, xt.data_ptr(), None, N, K, B, 1.0, 0.0, 0, 0.0, 1.0, st),
+                     "linear_bwd_w")
+        return gx, gW, g.sum(0), None
+
+
+def _mlp(seq, x):
+    mods = list(seq)
+    for j, m in enumerate(mods):
+        if isinstance(m, nn.Linear):
+            act = j + 1 < len(mods) and isinstance(mods[j + 1], nn.LeakyReLU)
+            x = _LinearFn.apply(x, m.weight, m.bias, act)
+    return x
+
+
+def _combine(ws, d_list, coef, mask, normalize):
+    """out_i = in_i + coef * d_i (or in_i + d_i/||d_i||); differentiable through torch ops on the
+    small [B, D] tensors only when grad is needed, native kernel otherwise."""
+    n = len(ws)
+    fill = next((t for t in d_list if t is not None), None)
+    if fill is None:
+        return list(ws)
+    d_list = [fill if t is None else t for t in d_list]
+    need_grad = torch.is_grad_enabled() and any(t.requires_grad for t in d_list)
+    if need_grad:
+        out = []
+        for i in range(n):
+            if (mask >> i) & 1:
+                d = d_list[i]
+                if normalize:
+                    d = d / torch.norm(d, dim=1, keepdim=True)
+                out.append(ws[i] + (coef * d if coef is not None else d))
+            else:
+                out.append(ws[i])
+        return out
+    blk, bs, ls = _as_latent_block(ws)
+    B, D = ws[0].shape
+    if all(t is d_list[0] for t in d_list):
+        dblk = d_list[0].detach().float().contiguous()
+        dbs, dls = dblk.stride(0), 0
+    else:
+        dblk = torch.stack([t.detach().float() for t in d_list], 1).contiguous()
+        dbs, dls = dblk.stride(0), dblk.stride(1)
+    c = coef.detach().float().reshape(-1).contiguous() if coef is not None else None
+    out = torch.empty(B, n, D, device=blk.device, dtype=torch.float32)
+    with torch.cuda.device(blk.device):
+        nt.check(nt.load().l2i_walk_combine(out.data_ptr(), blk.data_ptr(), bs, ls, dblk.data_ptr(), dbs, dls, nt.ptr(c), B, n, D,
+                                            mask, 1 if normalize else 0, nt.stream_ptr(blk.device)), "walk_combine")
+    return list(out.unbind(1))
+
+
+# ------------------------------------------------------------------------------------------------
+# walk modules (class / parameter names as in the reference)
+# ------------------------------------------------------------------------------------------------
+class WalkLinearMultiW(nn.Module):
+    """``out_i = in_i + alpha @ w[:, i, :]`` for every (or the selected) W+ layer."""
+
+    def __init__(self, dim_z, step, Nsliders, attrList):
+        super().__init__()
+        self.dim_z, self.step = dim_z, step
+        n_latent = (step + 1) * 2
+        # numpy global RNG, as the reference (transform_base.py:147)
+        self.w = nn.Parameter(torch.Tensor(np.random.normal(0.0, 0.02, [len(attrList), n_latent, dim_z])))
+
+    def forward(self, input, alpha, layers=None, name=None, index_=None):
+        n = len(input)
+        alpha = alpha.to(input[0].device)
+        out = _WalkLinearFn.apply(self.w, alpha, _layer_mask(n, layers), n, *input)
+        return list(out.unbind(1))
+
+
+class WalkMlpMultiW(nn.Module):
+    """``out_i = in_i + alpha[:, 0:1] * MLP(in_i)``, MLP = D -> 2D -> 2D -> D with LeakyReLU(0.2)."""
+
+    def __init__(self, dim_z, step, Nsliders, attrList):
+        super().__init__()
+        self.dim_z, self.step, self.Nsliders = dim_z, step, Nsliders
+        self.linear = nn.Sequential(nn.Linear(dim_z, 2 * dim_z), nn.LeakyReLU(0.2, True),
+                                    nn.Linear(2 * dim_z, 2 * dim_z), nn.LeakyReLU(0.2, True),
+                                    nn.Linear(2 * dim_z, dim_z))
+
+    def forward(self, input, alpha, layers=None, name=None, index_=None):
+        n = len(input)
+        al = alpha[:, 0:1].to(input[0].device)
+        mask = _layer_mask(n, layers)
+        cache, d = {}, []
+        for i in range(n):  # one MLP evaluation per distinct input tensor (the W+ list is usually one tensor)
+            if not (mask >> i) & 1:
+                d.append(None)
+                continue
+            key = id(input[i])
+            if key not in cache:
+                cache[key] = _mlp(self.linear, input[i])
+            d.append(cache[key])
+        return _combine(list(input), d, al, mask, normalize=False)
+
+
+class WalkNonLinearW(nn.Module):
+    """``e = embed(alpha[:, 0:1] x10)``; ``d = MLP([e, in_i])``; ``out_i = in_i + d/||d||``."""
+
+    def __init__(self, dim_z, step, Nsliders, attrList):
+        super().__init__()
+        self.dim_z, self.step, self.Nsliders = dim_z, step, Nsliders
+        self.embed = nn.Linear(10, dim_z // 2)
+        self.linear = nn.Sequential(nn.Linear(dim_z // 2 + dim_z, 2 * dim_z), nn.LeakyReLU(0.2, True),
+                                    nn.Linear(2 * dim_z, dim_z))
+
+    def forward(self, input, name=None, alpha=None, index_=None, layers=None):
+        if alpha is None and torch.is_tensor(name):  # keyword-less call walk(ws, alpha)
+            name, alpha = None, name
+        n = len(input)
+        al = alpha[:, 0:1].to(input[0].device)
+        e = _LinearFn.apply(al.repeat(1, 10), self.embed.weight, self.embed.bias, False)
+        mask = _layer_mask(n, layers)
+        cache, d = {}, []
+        for i in range(n):
+            if not (mask >> i) & 1:
+                d.append(None)
+                continue
+            key = id(input[i])
+            if key not in cache:
+                cache[key] = _mlp(self.linear, torch.cat([e, input[i].float()], 1))
+            d.append(cache[key])
+        return _combine(list(input), d, None, mask, normalize=layers is None)
+
+
+# ------------------------------------------------------------------------------------------------
+# orchestrator
+# ------------------------------------------------------------------------------------------------
+class _Module:
+    """Stands in for stylegan2.StyleGAN (stylegan2.py:19-64): holder of netG (and netD when built)."""
+
+    def __init__(self):
+        self.netG = None
+        self.netD = None
+
+
+class TransformGraph:
+    def __init__(self, lr, walk_type, nsliders, loss_type, eps, N_f, trainEmbed, attrList, attrTable, layers,
+                 stylegan_opts):
+        assert loss_type in ["l2", "lpips"], "unimplemented loss"
+        self.lr = lr
+        self.useGPU = constants.useGPU
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.img_size = constants.resolution
+        self.dim_z = constants.DIM_Z
+        self.BATCH_SIZE = constants.BATCH_SIZE
+        self.num_channels = constants.NUM_CHANNELS
+        self.module = self.get_stylegan2_module()
+        self.regressor, self.reg_optmizer = self.get_reg_module()
+        self.attrTable, self.attrList = attrTable, attrList
+        self.attrIdx = self.get_attr_idx()
+        self.Nsliders = nsliders
+        self.trainEmbed = trainEmbed
+        self.stylegan_opts = stylegan_opts
+        self.layers = layers
+        self.walk_type = walk_type
+        # (step + 1) * 2 == n_latent; the reference hard-codes step = 6 for 256 px (:285)
+        self.step = self.module.netG.log_size - 2
+        self.is_mlp = bool(getattr(constants, "walk_is_mlp", False))
+        latent = getattr(stylegan_opts, "latent", "w")
+        if walk_type == "linear":
+            if trainEmbed:
+                raise NotImplementedError("WalkEmbed is declared unused by the reference (transform_base.py:24-27)")
+            if latent != "w":
+                raise NotImplementedError("Not implemented setting of linear transformation for z")
+            cls = WalkMlpMultiW if self.is_mlp else WalkLinearMultiW
+            self.walk = cls(self.dim_z, self.step, nsliders, self.attrList).to(self.device)
+        elif "NN" in walk_type:
+            self.walk = WalkNonLinearW(self.dim_z, self.step, nsliders, self.attrList).to(self.device)
+        else:
+            raise NotImplementedError("Not implemented latent walk type: {}".format(walk_type))
+        self.optimizers = torch.optim.Adam(self.walk.parameters(), lr=self.lr, betas=(0.5, 0.99))
+
+    # ---- module construction ----------------------------------------------------------------
+    def get_stylegan2_module(self):
+        from .networks import Generator
+        gen = Generator(constants.resolution, constants.DIM_Z, 8)
+        if os.path.exists(constants.g_path):
+            ckpt = torch.load(constants.g_path, map_location="cpu", weights_only=False)
+            gen.load_state_dict(ckpt["g_ema"], strict=False)
+        elif not getattr(constants, "allow_random_init", True):
+            raise FileNotFoundError(constants.g_path)
+        dtype = {"fp32": torch.float32, "bf16": torch.bfloat16}[getattr(constants, "compute_dtype", "bf16")]
+        gen.set_native(dtype=dtype, max_batch=constants.BATCH_SIZE)
+        module = _Module()
+        module.netG = gen.to(self.device).eval()
+        return module
+
+    def get_reg_module(self):
+        import torchvision
+        model = torchvision.models.resnet50(weights=None)  # torch.hub needs network; same architecture
+        model.fc = torch.nn.Linear(2048, 40)
+        if os.path.exists(constants.reg_path):
+            ckpt = torch.load(constants.reg_path, map_location="cpu", weights_only=False)
+            model.load_state_dict(ckpt["model"])
+        elif not getattr(constants, "allow_random_init", True):
+            raise FileNotFoundError(constants.reg_path)
+        model = model.to(self.device).eval()
+        for p in model.parameters():
+            p.requires_grad_(False)  # frozen: only data gradients flow through R
+        return model, None
+
+    def get_attr_idx(self):
+        return [self.attrTable[i] for i in self.attrList]
+
+    # ---- hot path ----------------------------------------------------------------------------
+    def get_w(self, z, is_single=False):
+        w = self.module.netG.style(z)
+        return [w] if is_single else [w] * (self.step + 1) * 2
+
+    def get_logits(self, inputs_dict, reshape=True):
+        latent = getattr(self.stylegan_opts, "latent", "w")
+        if latent == "z":
+            out, _ = self.module.netG([inputs_dict["z"]])
+            return out
+        w = inputs_dict["w"]
+        w = torch.stack(list(w)).transpose(0, 1) if isinstance(w, (list, tuple)) else w.transpose(0, 1)
+        out, _ = self.module.netG(w, input_is_latent=True)
+        return out
+
+    def get_w_new_tensor(self, multi_ws, alpha, layers=None, name=None, trainEmbed=False, index_=None):
+        if isinstance(layers, str):  # train.py passes the raw --layers string (:174)
+            layers = None if layers in ("", "None") else [int(i) for i in layers.split(",")]
+        elif layers is not None:
+            layers = [int(i) for i in layers]
+        return self.walk(multi_ws, alpha=alpha, layers=layers)
+
+    def get_reg_preds(self, logit):
+        preds = self.regressor(logit)[:, self.attrIdx]
+        return preds.unsqueeze(1) if preds.ndim == 1 else preds
+
+    def get_alphas(self, alpha_org, alpha_target):
+        return alpha_target - alpha_org
+
+    def get_bce_loss(self, pred, y, eps=1e-12):
+        return -(y * pred.clamp(min=eps).log() + (1 - y) * (1 - pred).clamp(min=eps).log()).mean()
+
+    def get_reg_loss(self, feed_dict):
+        preds = self.regressor(feed_dict["logit"])[:, self.attrIdx]
+        return self.get_bce_loss(preds, feed_dict["alpha"].to(torch.double)).mean()
+
+    def optimizeParametersAll(self, feed_dict, trainEmbed, updateGAN, no_content_loss=False, no_gan_loss=False):
+        if not (no_content_loss and no_gan_loss):
+            raise NotImplementedError(
+                "the discriminator / VGG19 loss terms are outside the accelerated path (SURVEY section 2.1 rows 6, 8); "
+                "run with --no_content_loss --no_gan_loss")
+        self.optimizers.zero_grad()
+        loss = self.get_reg_loss(feed_dict)
+        loss.backward()
+        self.optimizers.step()
+        return loss
+
+    def save_multi_models(self, save_path_w, save_path_gan, trainEmbed=False, updateGAN=False, single_transform_name=None):
+        torch.save(self.walk, save_path_w + "_walk_module.ckpt")
+
+    def load_multi_models(self, save_path_w, save_path_gan, trainEmbed=False, updateGAN=False, single_transform_name=None):
+        import latent2im_b200
+        latent2im_b200.install_dropin()  # reference pickles name graphs.stylegan_v2_real.transform_base.<Walk>
+        self.walk = torch.load(save_path_w, map_location=self.device, weights_only=False)
+
+    def clip_ims(self, ims):
+        return np.uint8(np.clip(((ims + 1) / 2.0) * 255, 0, 255))
+
+    def apply_alpha(self, graph_inputs, alpha_to_graph, layers=None, name=None, trainEmbed=False, index_=None,
+                    given_w=None, return_uint8=False):
+        with torch.no_grad():
+            zs = graph_inputs["z"]
+            latent_w = given_w if given_w is not None else self.get_w(zs)
+            out_zs = self.get_logits({"w": latent_w})
+            alpha_org = self.get_reg_preds(out_zs)
+            target = torch.as_tensor(np.asarray(alpha_to_graph), dtype=torch.float32, device=self.device)
+            alpha_delta = self.get_alphas(alpha_org, target)
+            if index_ is not None:
+                col = index_ if len(self.attrIdx) == len(self.attrTable) else self.attrIdx.index(index_)
+                alpha_delta[:, col] = target[:, 0] - alpha_org[:, col]
+            latent_w_new = self.get_w_new_tensor(latent_w, alpha_delta, layers=layers, name=name, index_=index_)
+            best_im_out = self.get_logits({"w": latent_w_new})
+        return best_im_out, alpha_org, out_zs
+
+    def vis_multi_image_batch_alphas(self, graph_inputs, filename, alphas_to_graph, alphas_to_target, batch_start,
+                                     layers=None, name=None, wgt=False, wmask=False, trainEmbed=False, computeL2=False,
+                                     given_w=None, index_=None):
+        from latent2im_b200.utils import image
+        zs_batch = graph_inputs["z"]
+        panels = []
+        for ag, _ in zip(alphas_to_graph, alphas_to_target):
+            z = torch.Tensor(zs_batch).to(self.device)
+            im, alpha_org, _ = self.apply_alpha({"z": z}, ag, name=name, layers=layers, given_w=given_w, index_=index_)
+            u8 = torch.empty(im.shape[0], im.shape[2], im.shape[3], 3, device=im.device, dtype=torch.uint8)
+            nt.check(nt.load().l2i_image_to_uint8(u8.data_ptr(), im.contiguous().data_ptr(), im.shape[0], im.shape[2],
+                                                  im.shape[3], nt.stream_ptr(im.device)), "image_to_uint8")
+            panels.append(u8.cpu().numpy())
+        for ii in range(zs_batch.shape[0]):
+            a = alpha_org[ii, index_].item() if (index_ is not None and len(self.attrList) > 1) else alpha_org[ii].flatten()[0].item()
+            ims = np.stack([p[ii] for p in panels], axis=0)
+            fn = filename + "_sample{}".format(ii + batch_start) + ("_wgt" if wgt else "") + "_%.2f" % a
+            image.save_im(image.imgrid(ims, cols=len(alphas_to_graph)), fn)
+
+
+class PixelTransform(TransformGraph):
+    def __init__(self, *args, **kwargs):
+        TransformGraph.__init__(self, *args, **kwargs)

@@ -1,0 +1,131 @@
+"""GPU: the synthesis network and the latent side through the drop-in Generator vs the CPU oracle."""
+import pytest
+import torch
+
+from latent2im_b200.synthetic import load_synthetic, synthetic_noise, synthetic_z
+from oracle import GeneratorSpec, generator_forward_ref, mapping_ref
+from oracle.generator import clip_to_uint8_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _psnr(a, b):
+    return 10 * torch.log10(4.0 / ((a - b) ** 2).mean()).item()
+
+
+def _build(size, dim, n_mlp, seed=0):
+    from latent2im_b200.graphs.stylegan_v2_real.networks import Generator
+    gen = load_synthetic(Generator(size, dim, n_mlp), seed=seed)
+    sd = {k: v.double() for k, v in gen.state_dict().items()}
+    return gen.cuda(), sd, GeneratorSpec(size=size, style_dim=dim, n_mlp=n_mlp)
+
+
+def _latent(spec, batch, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(batch, spec.n_latent, spec.style_dim, generator=g)
+
+
+@pytest.mark.parametrize("size,dim,n_mlp,batch", [(8, 32, 2, 1), (16, 512, 8, 2), (32, 64, 2, 3), (64, 128, 1, 2)])
+def test_fp32_forward_matches_oracle(size, dim, n_mlp, batch):
+    gen, sd, spec = _build(size, dim, n_mlp)
+    gen.set_native(dtype=torch.float32)
+    lat = _latent(spec, batch)
+    noise = synthetic_noise(spec.num_layers, batch)
+    ref, inter = generator_forward_ref(sd, lat.double(), noise, spec, return_intermediates=True)
+    img, none = gen(lat.cuda(), input_is_latent=True, noise=[n.cuda() for n in noise])
+    assert none is None and img.shape == ref.shape and img.dtype == torch.float32
+    for k in range(spec.log_size - 1):
+        pass
+    err = (img.cpu().double() - ref).abs().max().item()
+    assert err <= 1e-3, f"fp32 max-abs {err:.3e}"
+
+
+def test_fp32_intermediates_and_skips():
+    gen, sd, spec = _build(16, 64, 2)
+    gen.set_native(dtype=torch.float32)
+    lat = _latent(spec, 2)
+    noise = synthetic_noise(spec.num_layers, 2)
+    ref, inter = generator_forward_ref(sd, lat.double(), noise, spec, return_intermediates=True)
+    gen(lat.cuda(), input_is_latent=True, noise=[n.cuda() for n in noise])
+    last = f"convs.{spec.num_layers - 3}"  # the newest materialised activation (ping-pong buffers)
+    got = gen.read_activation(last).cpu().double()
+    assert (got - inter[last]).abs().max() <= 1e-3
+    k = spec.log_size - 2
+    got = gen.read_activation(f"skip.{k}").cpu().double()
+    assert (got - inter[f"to_rgbs.{k - 1}"]).abs().max() <= 1e-3
+
+
+@pytest.mark.parametrize("size,dim,n_mlp,batch", [(16, 512, 8, 2), (64, 128, 1, 2), (128, 64, 1, 1)])
+def test_bf16_forward_psnr(size, dim, n_mlp, batch):
+    gen, sd, spec = _build(size, dim, n_mlp)
+    gen.set_native(dtype=torch.bfloat16)
+    lat = _latent(spec, batch)
+    noise = synthetic_noise(spec.num_layers, batch)
+    ref = generator_forward_ref(sd, lat.double(), noise, spec)
+    img, _ = gen(lat.cuda(), input_is_latent=True, noise=[n.cuda() for n in noise])
+    psnr = _psnr(img.cpu().double(), ref)
+    assert psnr >= 45.0, f"bf16 PSNR {psnr:.1f} dB"
+
+
+def test_noise_broadcast_and_registered_buffers():
+    gen, sd, spec = _build(16, 32, 1)
+    gen.set_native(dtype=torch.float32)
+    lat = _latent(spec, 3)
+    noise = [sd[f"noises.noise_{i}"] for i in range(spec.num_layers)]
+    ref = generator_forward_ref(sd, lat.double(), noise, spec)
+    img, _ = gen(lat.cuda(), input_is_latent=True, randomize_noise=False)
+    assert (img.cpu().double() - ref).abs().max() <= 1e-3
+
+
+def test_randomized_noise_draws_reference_stream():
+    """noise=None: tensors are drawn [B,1,H,W] float32 in execution order from the CUDA generator."""
+    gen, sd, spec = _build(16, 32, 1)
+    gen.set_native(dtype=torch.float32)
+    lat = _latent(spec, 2).cuda()
+    torch.manual_seed(123)
+    img, _ = gen(lat, input_is_latent=True)
+    torch.manual_seed(123)
+    expect = [torch.empty(2, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2), device="cuda").normal_() for i in range(spec.num_layers)]
+    drawn = gen._last[2]
+    assert all(torch.equal(a, b) for a, b in zip(drawn, expect))
+    img2, _ = gen(lat, input_is_latent=True, noise=expect)
+    assert torch.equal(img, img2)
+
+
+def test_mapping_and_style_call():
+    gen, sd, spec = _build(16, 512, 8)
+    z = torch.tensor(synthetic_z(5, 0, 512), dtype=torch.float32)
+    ref = mapping_ref(sd, z.double(), spec)
+    w = gen.style(z.cuda())
+    assert torch.allclose(w.cpu().double(), ref, atol=1e-4, rtol=1e-4)
+    assert torch.equal(w, gen.get_latent(z.cuda()))
+
+
+def test_uint8_epilogue_truncates_like_reference():
+    gen, sd, spec = _build(16, 32, 1)
+    gen.set_native(dtype=torch.float32)
+    lat = _latent(spec, 2)
+    noise = synthetic_noise(spec.num_layers, 2)
+    img, u8 = gen.synthesize(lat.cuda(), noise=[n.cuda() for n in noise], want_uint8=True)
+    expect = clip_to_uint8_ref(img.cpu()).permute(0, 2, 3, 1)
+    assert torch.equal(u8.cpu(), expect)
+
+
+def test_z_path_and_batch_growth():
+    gen, sd, spec = _build(16, 32, 2)
+    gen.set_native(dtype=torch.float32, max_batch=1)
+    z = torch.randn(4, 32)
+    noise = synthetic_noise(spec.num_layers, 4)
+    img, lat = gen([z.cuda()], return_latents=True, noise=[n.cuda() for n in noise])
+    w = mapping_ref(sd, z.double(), spec)
+    ref = generator_forward_ref(sd, w[:, None].repeat(1, spec.n_latent, 1), noise, spec)
+    assert lat.shape == (4, spec.n_latent, 32)
+    assert (img.cpu().double() - ref).abs().max() <= 1e-3
+
+
+def test_errors_are_loud():
+    gen, sd, spec = _build(16, 32, 1)
+    with pytest.raises(RuntimeError):
+        gen(torch.randn(1, spec.n_latent, 32), input_is_latent=True)  # CPU tensor
+    with pytest.raises(RuntimeError):
+        gen(torch.randn(1, 3, 32).cuda(), input_is_latent=True)  # wrong n_latent

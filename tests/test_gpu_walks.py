@@ -1,0 +1,100 @@
+"""GPU: walk modules (drop-in classes over the native walk kernels) vs the CPU oracle, incl. gradients."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.walks import walk_linear_ref, walk_mlp_ref, walk_nonlinear_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods():
+    from latent2im_b200.graphs.stylegan_v2_real import transform_base as tb
+    return tb
+
+
+def _seq_params(seq):
+    return [(m.weight.detach().cpu().double(), m.bias.detach().cpu().double()) for m in seq if isinstance(m, torch.nn.Linear)]
+
+
+@pytest.mark.parametrize("shared", [True, False])
+@pytest.mark.parametrize("layers", [None, [0, 3]])
+def test_walk_linear_forward_and_grad(shared, layers):
+    tb = _mods()
+    np.random.seed(0)
+    walk = tb.WalkLinearMultiW(64, 2, 1, ["a", "b"]).cuda()
+    B = 3
+    base = torch.randn(B, 64, device="cuda")
+    ws = [base] * 6 if shared else [torch.randn(B, 64, device="cuda") for _ in range(6)]
+    alpha = torch.randn(B, 2, device="cuda")
+    out = walk(ws, alpha, layers=layers)
+    ref = walk_linear_ref([w.cpu().double() for w in ws], alpha.cpu().double(), walk.w.detach().cpu().double(), layers)
+    for a, b in zip(out, ref):
+        assert torch.allclose(a.detach().cpu().double(), b, atol=1e-5)
+    probe = torch.randn(B, 6, 64, device="cuda")
+    (torch.stack(out, 1) * probe).sum().backward()
+    wr = walk.w.detach().cpu().double().requires_grad_(True)
+    ref2 = walk_linear_ref([w.cpu().double() for w in ws], alpha.cpu().double(), wr, layers)
+    (torch.stack(ref2, 1) * probe.cpu().double()).sum().backward()
+    assert torch.allclose(walk.w.grad.cpu().double(), wr.grad, atol=1e-4)
+
+
+def test_walk_mlp_forward_and_grad():
+    tb = _mods()
+    torch.manual_seed(0)
+    walk = tb.WalkMlpMultiW(32, 1, 1, ["a"]).cuda()
+    base = torch.randn(4, 32, device="cuda")
+    ws = [base] * 4
+    alpha = torch.randn(4, 1, device="cuda")
+    params = _seq_params(walk.linear)
+    with torch.no_grad():
+        out = walk(ws, alpha)
+    ref = walk_mlp_ref([w.cpu().double() for w in ws], alpha.cpu().double(), params)
+    for a, b in zip(out, ref):
+        assert torch.allclose(a.cpu().double(), b, atol=1e-4)
+    with torch.no_grad():
+        out = walk(ws, alpha, layers=[1, 2])
+    ref = walk_mlp_ref([w.cpu().double() for w in ws], alpha.cpu().double(), params, layers=[1, 2])
+    for a, b in zip(out, ref):
+        assert torch.allclose(a.cpu().double(), b, atol=1e-4)
+    # gradients w.r.t. the MLP parameters
+    out = walk(ws, alpha)
+    probe = torch.randn(4, 4, 32, device="cuda")
+    (torch.stack(out, 1) * probe).sum().backward()
+    pr = [(w.clone().requires_grad_(True), b.clone().requires_grad_(True)) for w, b in params]
+    ref = walk_mlp_ref([w.cpu().double() for w in ws], alpha.cpu().double(), pr)
+    (torch.stack(ref, 1) * probe.cpu().double()).sum().backward()
+    lin = [m for m in walk.linear if isinstance(m, torch.nn.Linear)]
+    for m, (w, b) in zip(lin, pr):
+        assert torch.allclose(m.weight.grad.cpu().double(), w.grad, atol=1e-3, rtol=1e-3)
+        assert torch.allclose(m.bias.grad.cpu().double(), b.grad, atol=1e-3, rtol=1e-3)
+
+
+def test_walk_nonlinear_forward():
+    tb = _mods()
+    torch.manual_seed(1)
+    walk = tb.WalkNonLinearW(32, 1, 1, ["a"]).cuda()
+    ws = [torch.randn(3, 32, device="cuda") for _ in range(4)]
+    alpha = torch.randn(3, 1, device="cuda")
+    emb = (walk.embed.weight.detach().cpu().double(), walk.embed.bias.detach().cpu().double())
+    params = _seq_params(walk.linear)
+    with torch.no_grad():
+        out = walk(ws, alpha=alpha)                       # the keyword call get_w_new_tensor makes
+        out_l = walk(ws, None, alpha, None, layers=[0, 2])  # the reference's positional signature
+    ref = walk_nonlinear_ref([w.cpu().double() for w in ws], alpha.cpu().double(), emb, params)
+    ref_l = walk_nonlinear_ref([w.cpu().double() for w in ws], alpha.cpu().double(), emb, params, layers=[0, 2])
+    for a, b in zip(out, ref):
+        assert torch.allclose(a.cpu().double(), b, atol=1e-4)
+    for a, b in zip(out_l, ref_l):
+        assert torch.allclose(a.cpu().double(), b, atol=1e-4)
+
+
+def test_walk_pickle_roundtrip_under_reference_module_path(tmp_path):
+    import latent2im_b200
+    latent2im_b200.install_dropin()
+    from graphs.stylegan_v2_real.transform_base import WalkLinearMultiW  # reference import path
+    walk = WalkLinearMultiW(16, 1, 1, ["a"])
+    p = tmp_path / "model_w_0_walk_module.ckpt"
+    torch.save(walk, p)
+    back = torch.load(p, weights_only=False)
+    assert torch.equal(back.w, walk.w)
