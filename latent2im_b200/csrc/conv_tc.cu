@@ -1,13 +1,484 @@
-// tcgen05 / TMEM / TMA implicit-GEMM modulated convolution (bf16 operands, fp32 accumulation).
-// Placeholder until the kernel lands: reports "unsupported" so the launcher uses the CUDA-core path.
+// tcgen05 / TMEM / TMA implicit-GEMM modulated convolution for sm_100a (bf16 operands, fp32 accumulate).
+//
+// GEMM view: M = output pixels (a 128-row tile is a bw x bh x bb box of the NHWC activation),
+// N = output channels, K = taps x Cin.  The A operand needs no im2col buffer: for every
+// (tap, 64-channel chunk) one 4-D TMA box load at the tap-shifted pixel coordinate lands a
+// [128 x 64] bf16 K-major tile in shared memory, out-of-bounds pixels (the conv padding) are
+// zero-filled by the TMA unit.  B is the packed weight [tap][Cout][Cin] (3-D TMA).  Both use the
+// 128-byte swizzle so the UMMA shared-memory descriptors are the canonical K-major SW128 layout.
+//
+// Warp roles (256 threads, one CTA per SM, persistent over tiles):
+//   warp 0   TMA producer          warp 1   tcgen05.mma issuer (one elected lane)
+//   warp 2   TMEM allocator        warps 4-7 epilogue: tcgen05.ld -> demod/noise/bias/lrelu/
+//                                           next-style scale/ToRGB/skip -> global stores
+// Pipelines: smem ring (full/empty mbarriers, TMA <-> MMA) and a 2-deep TMEM accumulator ring
+// (tmem_full/tmem_empty, MMA <-> epilogue) so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+
 #include "conv_common.cuh"
 
 namespace l2i {
 
-bool conv_tc_supported(const ConvGeom&, const EpiParams&) { return false; }
+namespace {
 
-int launch_conv_tc(const void*, const __nv_bfloat16*, const ConvGeom&, const EpiParams&, cudaStream_t) {
-  set_error("conv_tc: kernel not built");
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols));
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate, issued by one thread
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp): rows are
+// swizzle_bytes wide, 8-row groups are `sbo` bytes apart, version = 1 (Blackwell).
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);              // start address  [0,14)
+  d |= (uint64_t)0 << 16;                                  // leading byte offset (unused: one atom along K)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;        // stride byte offset [32,46)
+  d |= (uint64_t)1 << 46;                                  // version [46,48)
+  d |= (uint64_t)(layout_type & 7) << 61;                  // layout type [61,64): 2 = SW128, 4 = SW64
+  return d;
+}
+
+// cute::UMMA::InstrDescriptor for kind::f16: c=F32 (1<<4), a=b=BF16 (1<<7, 1<<10), K-major A and B,
+// n_dim = N>>3 at bit 17, m_dim = M>>4 at bit 24.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct TcParams {
+  int B, H, W, Cin, Cout;
+  int OH, OW, nphase, out_scale, out_H, out_W;
+  TapList taps[4];
+  int bw, bh, bb;                 // M-tile box (pixels x rows x samples), bw*bh*bb == 128
+  int tiles_x, tiles_y, tiles_b, tiles_n;
+  int total_tiles;
+  EpiParams e;
+};
+
+constexpr int kBlockM = 128;
+constexpr int kNumThreads = 256;
+constexpr int kEpiWarp0 = 4;
+
+template <int BLOCK_N, int BLOCK_K, int STAGES>
+struct SmemLayout {
+  static constexpr int kABytes = kBlockM * BLOCK_K * 2;
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarrierBytes = 256;
+  static constexpr int kTotal = STAGES * kStageBytes + kBarrierBytes + 1024;  // + alignment slack
+};
+
+template <int BLOCK_N, int BLOCK_K, int STAGES>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ TcParams p) {
+  using L = SmemLayout<BLOCK_N, BLOCK_K, STAGES>;
+  constexpr uint32_t kSwizzleBytes = BLOCK_K * 2;                 // 128 or 64
+  constexpr uint32_t kLayoutType = kSwizzleBytes == 128 ? 2u : 4u;
+  constexpr uint32_t kSBO = 8 * kSwizzleBytes;
+  constexpr uint32_t kTmemCols = (2 * BLOCK_N) < 32 ? 32 : 2 * BLOCK_N;  // two accumulator stages
+  constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM, BLOCK_N);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * L::kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_smem = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_base_smem, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  const int kchunks = p.Cin / BLOCK_K;
+  const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_b;
+
+  auto decode = [&](int tile, int& phase, int& x0, int& y0, int& b0, int& nt) {
+    nt = tile % p.tiles_n;
+    int r = tile / p.tiles_n;
+    const int mt = r % tiles_m;
+    phase = r / tiles_m;
+    const int tx = mt % p.tiles_x;
+    const int ty = (mt / p.tiles_x) % p.tiles_y;
+    const int tb = mt / (p.tiles_x * p.tiles_y);
+    x0 = tx * p.bw; y0 = ty * p.bh; b0 = tb * p.bb;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase_bit = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int ph, x0, y0, b0, nt;
+        decode(tile, ph, x0, y0, b0, nt);
+        const TapList& taps = p.taps[ph];
+        for (int t = 0; t < taps.n; ++t) {
+          for (int kc = 0; kc < kchunks; ++kc) {
+            mbar_wait(&empty_bar[stage], phase_bit ^ 1);
+            uint8_t* sa = smem + stage * L::kStageBytes;
+            uint8_t* sb = sa + L::kABytes;
+            mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+            tma_load_4d(sa, &tmap_a, &full_bar[stage], kc * BLOCK_K, x0 + taps.dx[t], y0 + taps.dy[t], b0);
+            tma_load_3d(sb, &tmap_b, &full_bar[stage], kc * BLOCK_K, nt * BLOCK_N, taps.wtap[t]);
+            if (++stage == STAGES) { stage = 0; phase_bit ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase_bit = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int ph, x0, y0, b0, nt;
+        decode(tile, ph, x0, y0, b0, nt);
+        const int nk = p.taps[ph].n * kchunks;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(&full_bar[stage], phase_bit);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            const uint64_t adesc = make_kmajor_desc(sa + k * 32, kSBO, kLayoutType);
+            const uint64_t bdesc = make_kmajor_desc(sb + k * 32, kSBO, kLayoutType);
+            umma_bf16(tmem_d, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase_bit ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);      // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue =====================
+    const EpiParams& e = p.e;
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;          // tile row == TMEM lane
+    const float nw = (e.noise != nullptr && e.noise_w != nullptr) ? __ldg(e.noise_w) : 0.f;
+    const int64_t plane = (int64_t)p.out_H * p.out_W;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int ph, x0, y0, b0, nt;
+      decode(tile, ph, x0, y0, b0, nt);
+      const int lx = row % p.bw, ly = (row / p.bw) % p.bh, lb = row / (p.bw * p.bh);
+      const int ox = x0 + lx, oy = y0 + ly, b = b0 + lb;
+      const bool valid = ox < p.OW && oy < p.OH && b < p.B;
+      const int Y = oy * p.out_scale + (ph >> 1), X = ox * p.out_scale + (ph & 1);
+      const int bb = valid ? b : 0;
+      const float* demod = e.demod + (int64_t)bb * e.demod_bs;
+      const float* s_next = e.s_next ? e.s_next + (int64_t)bb * e.s_next_bs : nullptr;
+      const float* wr = e.wr ? e.wr + (int64_t)bb * e.wr_bs : nullptr;
+      float nz = 0.f;
+      if (e.mode == 0 && e.noise != nullptr && valid) nz = nw * __ldg(e.noise + (int64_t)b * e.noise_bs + (int64_t)Y * p.out_W + X);
+      __nv_bfloat16* outp = nullptr;
+      if (valid && e.out != nullptr && (e.mode == 1 || s_next != nullptr))
+        outp = (__nv_bfloat16*)e.out + (((int64_t)b * p.out_H + Y) * p.out_W + X) * p.Cout + nt * BLOCK_N;
+      float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        tmem_ld_wait();
+        const int co0 = nt * BLOCK_N + c0;
+        uint32_t packed[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float o[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int co = co0 + j + h;
+            float x = __uint_as_float(v[j + h]) * __ldg(demod + co);
+            if (e.mode == 0) {
+              x = x + nz + __ldg(e.bias + co);
+              x = (x > 0.f ? x : 0.2f * x) * 1.4142135623730951f;
+              if (wr != nullptr) {
+                rgb0 = fmaf(__ldg(wr + co), x, rgb0);
+                rgb1 = fmaf(__ldg(wr + p.Cout + co), x, rgb1);
+                rgb2 = fmaf(__ldg(wr + 2 * p.Cout + co), x, rgb2);
+              }
+              if (s_next != nullptr) x *= __ldg(s_next + co);
+            }
+            o[h] = x;
+          }
+          __nv_bfloat162 pk = __floats2bfloat162_rn(o[0], o[1]);
+          packed[j >> 1] = *reinterpret_cast<uint32_t*>(&pk);
+        }
+        if (outp != nullptr) {
+          uint4* dst = reinterpret_cast<uint4*>(outp + c0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) dst[k] = make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
+        }
+      }
+      // all TMEM reads of this accumulator stage are complete (wait::ld above): hand it back
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+
+      if (e.mode == 0 && wr != nullptr && valid) {
+        const float r3[3] = {rgb0, rgb1, rgb2};
+        if (e.fused_skip) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float val = r3[c] + __ldg(e.rgb_bias + c);
+            if (e.skip_in != nullptr)
+              val += upsample2x_at(e.skip_in + ((int64_t)b * 3 + c) * (plane / 4), p.out_H / 2, p.out_W / 2, Y, X, e.fir);
+            e.skip_out[((int64_t)b * 3 + c) * plane + (int64_t)Y * p.out_W + X] = val;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            e.rgb_part[(((int64_t)nt * p.B + b) * 3 + c) * plane + (int64_t)Y * p.out_W + X] = r3[c];
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)sym;
+  }
+  return fn;
+}
+
+int make_tmap(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box, CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("conv_tc: cuTensorMapEncodeTiled entry point not available");
+    return L2I_ERR_CUDA;
+  }
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i + 1];
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("conv_tc: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    return L2I_ERR_CUDA;
+  }
+  return L2I_OK;
+}
+
+template <int BLOCK_N, int BLOCK_K, int STAGES>
+int launch_variant(const void* in, const __nv_bfloat16* w, const TcParams& p, cudaStream_t st) {
+  using L = SmemLayout<BLOCK_N, BLOCK_K, STAGES>;
+  static_assert(L::kTotal <= 227 * 1024, "shared memory budget");
+  CUtensorMap ta, tb;
+  const CUtensorMapSwizzle swz = BLOCK_K == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  {
+    const uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.B};
+    const uint64_t str[4] = {2, (uint64_t)p.Cin * 2, (uint64_t)p.W * p.Cin * 2, (uint64_t)p.H * p.W * p.Cin * 2};
+    const uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bb};
+    L2I_TRY(make_tmap(&ta, in, 4, dims, str, box, swz));
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)p.Cin, (uint64_t)p.Cout, 9};
+    const uint64_t str[3] = {2, (uint64_t)p.Cin * 2, (uint64_t)p.Cout * p.Cin * 2};
+    const uint32_t box[3] = {(uint32_t)BLOCK_K, (uint32_t)BLOCK_N, 1};
+    L2I_TRY(make_tmap(&tb, w, 3, dims, str, box, swz));
+  }
+  auto kern = conv_tc_kernel<BLOCK_N, BLOCK_K, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    L2I_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    attr_set = true;
+  }
+  const int grid = std::min(p.total_tiles, kNumSMs);
+  kern<<<grid, kNumThreads, L::kTotal, st>>>(ta, tb, p);
+  return check_launch("conv_tc");
+}
+
+int pick_block_n(int cout) { return cout >= 256 ? 256 : cout; }
+
+}  // namespace
+
+bool conv_tc_supported(const ConvGeom& g, const EpiParams& e) {
+  (void)e;
+  if (g.Cin % 32 != 0 || g.Cin < 32) return false;
+  const int bn = pick_block_n(g.Cout);
+  if (!(bn == 32 || bn == 64 || bn == 128 || bn == 256)) return false;
+  if (g.Cout % bn != 0) return false;
+  if (g.Cin < 64 && bn != 32) return false;  // only the (K=32, N=32) small variant is instantiated
+  if (get_encode_fn() == nullptr) return false;
+  return true;
+}
+
+int conv_tc_block_n(const ConvGeom& g) { return pick_block_n(g.Cout); }
+
+int launch_conv_tc(const void* in, const __nv_bfloat16* w, const ConvGeom& g, const EpiParams& e, cudaStream_t st) {
+  TcParams p{};
+  p.B = g.B; p.H = g.H; p.W = g.W; p.Cin = g.Cin; p.Cout = g.Cout;
+  p.OH = g.OH; p.OW = g.OW; p.nphase = g.nphase; p.out_scale = g.out_scale; p.out_H = g.out_H; p.out_W = g.out_W;
+  for (int i = 0; i < 4; ++i) p.taps[i] = g.taps[i];
+  p.e = e;
+  // M-tile box: up to 16 pixels wide, then rows, then samples, 128 rows in total
+  int bw = 1;
+  while (bw < 16 && bw < g.OW) bw <<= 1;
+  int bh = 1;
+  while (bw * bh < 128 && bh < g.OH) bh <<= 1;
+  int bb = 128 / (bw * bh);
+  p.bw = bw; p.bh = bh; p.bb = bb;
+  p.tiles_x = ceil_div(g.OW, bw); p.tiles_y = ceil_div(g.OH, bh); p.tiles_b = ceil_div(g.B, bb);
+  const int bn = pick_block_n(g.Cout);
+  p.tiles_n = g.Cout / bn;
+  const int64_t total = (int64_t)p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n * g.nphase;
+  if (total <= 0 || total > 0x7fffffff) {
+    set_error("conv_tc: bad tile count %lld", (long long)total);
+    return L2I_ERR_INVALID_ARG;
+  }
+  p.total_tiles = (int)total;
+  if (e.fused_skip && p.tiles_n != 1) {
+    set_error("conv_tc: fused skip needs a single N tile");
+    return L2I_ERR_INVALID_ARG;
+  }
+  if ((uintptr_t)in % 16 != 0 || (uintptr_t)w % 16 != 0) {
+    set_error("conv_tc: operands must be 16-byte aligned");
+    return L2I_ERR_INVALID_ARG;
+  }
+  if (g.Cin >= 64) {
+    switch (bn) {
+      case 256: return launch_variant<256, 64, 4>(in, w, p, st);
+      case 128: return launch_variant<128, 64, 6>(in, w, p, st);
+      case 64: return launch_variant<64, 64, 8>(in, w, p, st);
+      case 32: return launch_variant<32, 64, 8>(in, w, p, st);
+    }
+  } else if (bn == 32) {
+    return launch_variant<32, 32, 8>(in, w, p, st);
+  }
+  set_error("conv_tc: unsupported shape Cin=%d Cout=%d", g.Cin, g.Cout);
   return L2I_ERR_UNSUPPORTED;
 }
 

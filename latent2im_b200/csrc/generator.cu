@@ -16,6 +16,7 @@ namespace l2i {
 template <typename T> int launch_conv_simt(const void*, const float*, const ConvGeom&, const EpiParams&, cudaStream_t);
 int launch_conv_tc(const void* in, const __nv_bfloat16* w, const ConvGeom& g, const EpiParams& e, cudaStream_t st);
 bool conv_tc_supported(const ConvGeom& g, const EpiParams& e);
+int conv_tc_block_n(const ConvGeom& g);
 template <typename T>
 int launch_blur_act(void*, const void*, int, int, int, int, int, int, const float*, int64_t, const float*,
                     const float*, const float*, int64_t, const float*, cudaStream_t);
@@ -501,7 +502,7 @@ extern "C" int l2i_generator_forward(l2i_generator_t* g, const float* latent, in
     float* skip_dst = (final_rgb && image != nullptr) ? image : g->skip[skip_sel];
     e.skip_out = skip_dst;
     e.rgb_part = g->rgb_part;
-    const int n_tile = (f32 || g->conv_impl == 1 || !conv_tc_supported(geom, e)) ? 64 : 256;
+    const int n_tile = (f32 || g->conv_impl == 1 || !conv_tc_supported(geom, e)) ? 64 : conv_tc_block_n(geom);
     const int nparts = ceil_div(L.cout, n_tile);
     e.fused_skip = nparts == 1 ? 1 : 0;
     L2I_TRY(run_conv(g, L, g->act[cur], geom, e, st));

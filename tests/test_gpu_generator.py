@@ -129,3 +129,43 @@ def test_errors_are_loud():
         gen(torch.randn(1, spec.n_latent, 32), input_is_latent=True)  # CPU tensor
     with pytest.raises(RuntimeError):
         gen(torch.randn(1, 3, 32).cuda(), input_is_latent=True)  # wrong n_latent
+
+
+@pytest.mark.parametrize("size", [16, 32, 64])
+def test_product_path_against_reference_goldens(size):
+    """fp32 kernels vs the fixtures the UNMODIFIED reference produced on a B200 (max-abs <= 1e-3)."""
+    import os
+    import numpy as np
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_gpu_generator.npz")
+    z = np.load(path)
+    size_, dim, n_mlp, batch = [int(v) for v in z[f"s{size}_cfg"]]
+    gen, sd, spec = _build(size, dim, n_mlp, seed=size)
+    gen.set_native(dtype=torch.float32)
+    zz = torch.tensor(synthetic_z(batch, seed=size, dim_z=dim), dtype=torch.float32)
+    w = gen.style(zz.cuda())
+    assert torch.allclose(w.cpu(), torch.from_numpy(z[f"s{size}_w"]), atol=1e-4, rtol=1e-4)
+    lat = torch.from_numpy(z[f"s{size}_latent"]).cuda()
+    noise = [n.cuda() for n in synthetic_noise(spec.num_layers, batch, seed=2)]
+    img, _ = gen(lat, input_is_latent=True, noise=noise)
+    assert (img.cpu() - torch.from_numpy(z[f"s{size}_image"])).abs().max().item() <= 1e-3
+    img2, _ = gen(lat, input_is_latent=True, randomize_noise=False)
+    assert (img2.cpu() - torch.from_numpy(z[f"s{size}_image_fixed_noise"])).abs().max().item() <= 1e-3
+    gen.set_native(dtype=torch.bfloat16)
+    img3, _ = gen(lat, input_is_latent=True, noise=noise)
+    assert _psnr(img3.cpu().double(), torch.from_numpy(z[f"s{size}_image"]).double()) >= 45.0
+
+
+@pytest.mark.parametrize("size,batch", [(8, 1), (16, 3), (64, 2), (128, 1)])
+def test_tcgen05_conv_matches_cuda_core_conv(size, batch, monkeypatch):
+    """Same bf16 activations through the tcgen05 kernel and the CUDA-core kernel."""
+    from latent2im_b200.graphs.stylegan_v2_real.networks import Generator
+    spec = GeneratorSpec(size=size, style_dim=64, n_mlp=1)
+    lat = _latent(spec, batch).cuda()
+    noise = [n.cuda() for n in synthetic_noise(spec.num_layers, batch)]
+    imgs = {}
+    for impl in ("simt", "tc"):
+        monkeypatch.setenv("L2I_CONV_IMPL", impl)
+        gen = load_synthetic(Generator(size, 64, 1), seed=0).cuda()
+        gen.set_native(dtype=torch.bfloat16)
+        imgs[impl], _ = gen(lat, input_is_latent=True, noise=noise)
+    assert _psnr(imgs["tc"].double(), imgs["simt"].double()) >= 50.0

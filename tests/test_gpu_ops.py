@@ -100,9 +100,9 @@ def test_latent_kernels():
     w = torch.randn(A, L, D, generator=g)
     ref = torch.stack(walk_linear_ref([ws[:, i].double() for i in range(L)], alpha.double(), w.double(), layers=[0, 2, 5]), 1)
     out = torch.empty(B, L, D, device="cuda")
-    wsc = ws.cuda()
+    wsc, alc, wc = ws.cuda(), alpha.cuda(), w.cuda()  # keep the device buffers alive across the call
     mask = (1 << 0) | (1 << 2) | (1 << 5)
-    nt.check(lib.l2i_walk_linear_fwd(out.data_ptr(), wsc.data_ptr(), L * D, D, alpha.cuda().data_ptr(), w.cuda().data_ptr(),
+    nt.check(lib.l2i_walk_linear_fwd(out.data_ptr(), wsc.data_ptr(), L * D, D, alc.data_ptr(), wc.data_ptr(),
                                      B, A, L, D, mask, nt.stream_ptr()), "walk")
     assert torch.allclose(out.cpu().double(), ref, atol=1e-5)
     # linear + pixel norm
@@ -110,7 +110,8 @@ def test_latent_kernels():
     W = torch.randn(48, D, generator=g)
     bias = torch.randn(48, generator=g)
     y = torch.empty(B, 48, device="cuda")
-    nt.check(lib.l2i_linear_fwd(y.data_ptr(), 48, x.cuda().data_ptr(), D, W.cuda().data_ptr(), bias.cuda().data_ptr(), B, 48, D,
+    xc, Wc, bc = x.cuda(), W.cuda(), bias.cuda()
+    nt.check(lib.l2i_linear_fwd(y.data_ptr(), 48, xc.data_ptr(), D, Wc.data_ptr(), bc.data_ptr(), B, 48, D,
                                 0.5, 2.0, 1, 0.2, 1.5, nt.stream_ptr()), "linear")
     v = (x.double() @ W.double().t()) * 0.5 + bias.double() * 2.0
     v = torch.where(v > 0, v, 0.2 * v) * 1.5
