@@ -160,6 +160,15 @@ int l2i_generator_forward(l2i_generator_t* g, const float* latent, int64_t laten
 int l2i_generator_backward(l2i_generator_t* g, float* grad_latent, const float* grad_image,
                            int batch, void* stream);
 
+/* Per-segment device timing of the last forward (CUDA events recorded on the forward's stream
+ * around each layer's kernels).  profile_entry() waits for the segment's end event - it is the one
+ * call of this library that blocks the host.  kind: 0 conv, 1 blur_act, 2 skip/rgb/image, 3 styles.
+ * flops / bytes are the ALGORITHMIC figures of the reference formulation. */
+int l2i_generator_set_profiling(l2i_generator_t* g, int enable);
+int l2i_generator_profile_count(l2i_generator_t* g);
+int l2i_generator_profile_entry(l2i_generator_t* g, int i, char* name, int name_len, int* kind, float* ms,
+                                double* flops, double* bytes);
+
 /* Debug / test taps: copies an internal activation of the last forward as fp32 NCHW.
  * name: "conv1", "convs.<j>", "skip.<k>" (k = 0 is to_rgb1).  out must hold the full tensor. */
 int l2i_generator_read_activation(l2i_generator_t* g, const char* name, float* out, int64_t numel,

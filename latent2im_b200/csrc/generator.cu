@@ -95,6 +95,33 @@ struct l2i_generator {
 
   std::vector<void*> allocs;
   size_t elem_size() const { return dtype == L2I_F32 ? 4 : 2; }
+
+  // optional per-segment timing (CUDA events on the caller's stream)
+  struct Segment {
+    std::string name;
+    int kind;          // 0 conv (tensor / FFMA bound), 1 blur_act, 2 skip / rgb, 3 styles & misc
+    double flops, bytes;
+    cudaEvent_t ev0, ev1;
+  };
+  bool profiling = false;
+  std::vector<Segment> segs;
+  size_t seg_used = 0;
+  Segment* seg_begin(const std::string& name, int kind, double flops, double bytes, cudaStream_t st) {
+    if (!profiling) return nullptr;
+    if (seg_used == segs.size()) {
+      Segment sg;
+      cudaEventCreate(&sg.ev0);
+      cudaEventCreate(&sg.ev1);
+      segs.push_back(sg);
+    }
+    Segment& sg = segs[seg_used++];
+    sg.name = name; sg.kind = kind; sg.flops = flops; sg.bytes = bytes;
+    cudaEventRecord(sg.ev0, st);
+    return &sg;
+  }
+  void seg_end(Segment* sg, cudaStream_t st) {
+    if (sg) cudaEventRecord(sg->ev1, st);
+  }
 };
 
 namespace {
@@ -344,6 +371,7 @@ extern "C" int l2i_generator_create(l2i_generator_t** out, int size, int style_d
 extern "C" void l2i_generator_destroy(l2i_generator_t* g) {
   if (!g) return;
   for (void* p : g->allocs) cudaFree(p);
+  for (auto& sg : g->segs) { cudaEventDestroy(sg.ev0); cudaEventDestroy(sg.ev1); }
   delete g;
 }
 
@@ -435,7 +463,10 @@ extern "C" int l2i_generator_forward(l2i_generator_t* g, const float* latent, in
       L2I_REQUIRE(noise_batch != nullptr && (noise_batch[i] == 1 || noise_batch[i] == B),
                   "generator_forward: noise[%d] batch must be 1 or %d", i, B);
 
+  g->seg_used = 0;
+  const double es = (double)g->elem_size();
   // 1. styles for every modulated conv, demodulation coefficients, ToRGB effective weights
+  auto* sg_styles = g->seg_begin("styles", 3, 2.0 * B * g->s_rows * D, 4.0 * g->s_rows * D, st);
   L2I_TRY(launch_gather_latent(g->latent_buf, latent, latent_batch_stride, latent_layer_stride, B, g->n_latent, D, st));
   L2I_TRY(launch_linear(g->s_all, g->s_rows, g->latent_buf, (int64_t)g->n_latent * D, g->row_xoff, g->mod_w_all,
                         g->mod_b_all, B, g->s_rows, D, 1.f, 1.f, 0, 0.f, 1.f, st));
@@ -450,6 +481,7 @@ extern "C" int l2i_generator_forward(l2i_generator_t* g, const float* latent, in
     if (f32) L2I_TRY(launch_const_input<float>(g->act[cur], P(g, "input.input"), g->s_all + L.s_off, g->s_rows, B, L.cin, 16, st));
     else L2I_TRY(launch_const_input<__nv_bfloat16>(g->act[cur], P(g, "input.input"), g->s_all + L.s_off, g->s_rows, B, L.cin, 16, st));
   }
+  g->seg_end(sg_styles, st);
 
   // 3. layers
   const float* skip_prev = nullptr;
@@ -475,12 +507,19 @@ extern "C" int l2i_generator_forward(l2i_generator_t* g, const float* latent, in
       geom.out_H = geom.out_W = 2 * L.res_in + 2;
       for (int ph = 0; ph < 4; ++ph) geom.taps[ph] = upconv_taps(ph >> 1, ph & 1);
       e.mode = 1; e.out = g->tbuf;
+      const double px_in = (double)B * L.res_in * L.res_in, px_out = (double)B * L.res_out * L.res_out;
+      const double px_t = (double)B * (2.0 * L.res_in + 1) * (2.0 * L.res_in + 1);
+      auto* sg_c = g->seg_begin(L.name + "/upconv", 0, 2.0 * 9 * L.cin * L.cout * px_in,
+                                (px_in * L.cin + px_t * L.cout) * es, st);
       L2I_TRY(run_conv(g, L, g->act[cur], geom, e, st));
+      g->seg_end(sg_c, st);
+      auto* sg_b = g->seg_begin(L.name + "/blur_act", 1, 0.0, (px_t + px_out) * L.cout * es + px_out * 4.0, st);
       void* dst = g->act[cur ^ 1];
       if (f32) L2I_TRY(launch_blur_act<float>(dst, g->tbuf, B, L.res_out, L.res_out, L.cout, geom.out_H, geom.out_W, nz, nz_bs, nz_w,
                                               P(g, L.name + ".activate.bias"), s_next, g->s_rows, g->fir, st));
       else L2I_TRY(launch_blur_act<__nv_bfloat16>(dst, g->tbuf, B, L.res_out, L.res_out, L.cout, geom.out_H, geom.out_W, nz, nz_bs,
                                                   nz_w, P(g, L.name + ".activate.bias"), s_next, g->s_rows, g->fir, st));
+      g->seg_end(sg_b, st);
       cur ^= 1;
       g->conv_out[li] = g->act[cur];
       continue;
@@ -505,9 +544,16 @@ extern "C" int l2i_generator_forward(l2i_generator_t* g, const float* latent, in
     const int n_tile = (f32 || g->conv_impl == 1 || !conv_tc_supported(geom, e)) ? 64 : conv_tc_block_n(geom);
     const int nparts = ceil_div(L.cout, n_tile);
     e.fused_skip = nparts == 1 ? 1 : 0;
+    const double px = (double)B * L.res_out * L.res_out;
+    auto* sg_c = g->seg_begin(L.name + "/conv+torgb", 0, 2.0 * (9.0 * L.cin + 3.0) * L.cout * px,
+                              px * L.cin * es + (s_next ? px * L.cout * es : 0.0) + px * 4.0 + px * 12.0 * (e.fused_skip ? 1.25 : 1.0), st);
     L2I_TRY(run_conv(g, L, g->act[cur], geom, e, st));
-    if (!e.fused_skip)
+    g->seg_end(sg_c, st);
+    if (!e.fused_skip) {
+      auto* sg_s = g->seg_begin(R.name + "/skip", 2, 0.0, px * 12.0 * (nparts + 1.25), st);
       L2I_TRY(launch_skip_combine(skip_dst, g->rgb_part, nparts, e.rgb_bias, skip_prev, B, L.res_out, L.res_out, g->fir, st));
+      g->seg_end(sg_s, st);
+    }
     if (s_next) cur ^= 1;
     g->conv_out[li] = s_next ? g->act[cur] : nullptr;
     g->skip_out[rgb_i] = skip_dst;
@@ -515,8 +561,36 @@ extern "C" int l2i_generator_forward(l2i_generator_t* g, const float* latent, in
     skip_sel ^= 1;
     ++rgb_i;
   }
-  if (image_u8 != nullptr) L2I_TRY(l2i_image_to_uint8(image_u8, skip_prev, B, g->size, g->size, stream));
+  if (image_u8 != nullptr) {
+    auto* sg_u = g->seg_begin("image_to_uint8", 2, 0.0, (double)B * g->size * g->size * 15.0, st);
+    L2I_TRY(l2i_image_to_uint8(image_u8, skip_prev, B, g->size, g->size, stream));
+    g->seg_end(sg_u, st);
+  }
   g->last_batch = B;
+  return L2I_OK;
+}
+
+extern "C" int l2i_generator_set_profiling(l2i_generator_t* g, int enable) {
+  L2I_REQUIRE(g, "generator_set_profiling: null generator");
+  g->profiling = enable != 0;
+  g->seg_used = 0;
+  return L2I_OK;
+}
+
+extern "C" int l2i_generator_profile_count(l2i_generator_t* g) { return g ? (int)g->seg_used : -1; }
+
+extern "C" int l2i_generator_profile_entry(l2i_generator_t* g, int i, char* name, int name_len, int* kind, float* ms,
+                                           double* flops, double* bytes) {
+  L2I_REQUIRE(g && i >= 0 && (size_t)i < g->seg_used, "generator_profile_entry: index out of range");
+  auto& sg = g->segs[i];
+  L2I_CUDA_TRY(cudaEventSynchronize(sg.ev1));
+  float t = 0.f;
+  L2I_CUDA_TRY(cudaEventElapsedTime(&t, sg.ev0, sg.ev1));
+  if (name && name_len > 0) { std::strncpy(name, sg.name.c_str(), name_len - 1); name[name_len - 1] = 0; }
+  if (kind) *kind = sg.kind;
+  if (ms) *ms = t;
+  if (flops) *flops = sg.flops;
+  if (bytes) *bytes = sg.bytes;
   return L2I_OK;
 }
 

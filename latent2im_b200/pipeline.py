@@ -1,0 +1,68 @@
+"""End-to-end latent-walk edit: host latents in, host uint8 images out.
+
+This is the call a user of the accelerated path makes for the forward-only edit workload
+(BASELINE.json configs[1]): ``z -> w = style(z) -> w' = walk(w, alpha) -> G(w') -> uint8 panels``,
+i.e. the body of the reference's ``apply_alpha`` + the host-side ``clip((x+1)/2*255)`` of
+``vis_multi_image_batch_alphas`` (transform_base.py:554-603, 625-626) with the attribute regressor
+factored out (``alpha`` is the walk step epsilon).  Host buffers are
+pinned once; every call copies z / alpha to the device and the uint8 result back on the current
+stream.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+class EditPipeline:
+    def __init__(self, generator, walk, batch: int, n_attr: int = 1, device=None):
+        self.gen, self.walk, self.batch = generator, walk, batch
+        self.device = torch.device(device) if device is not None else generator.input.input.device
+        if self.device.type != "cuda":
+            raise RuntimeError("EditPipeline needs a CUDA device (there is no CPU fallback)")
+        dim, size = generator.style_dim, generator.size
+        self.z_host = torch.empty(batch, dim, dtype=torch.float32).pin_memory()
+        self.alpha_host = torch.empty(batch, n_attr, dtype=torch.float32).pin_memory()
+        self.out_host = torch.empty(batch, size, size, 3, dtype=torch.uint8).pin_memory()
+        self.z_dev = torch.empty(batch, dim, dtype=torch.float32, device=self.device)
+        self.alpha_dev = torch.empty(batch, n_attr, dtype=torch.float32, device=self.device)
+        generator.set_native(max_batch=batch)
+
+    @property
+    def h2d_bytes(self) -> int:
+        return self.z_host.numel() * 4 + self.alpha_host.numel() * 4
+
+    @property
+    def d2h_bytes(self) -> int:
+        return self.out_host.numel()
+
+    @torch.no_grad()
+    def edit_device(self, z_dev, alpha_dev, layers=None, noise=None, want_uint8=False):
+        """Device-resident part: mapping -> walk -> synthesis.  Returns the fp32 image (reference
+        return value) or the uint8 NHWC image."""
+        w = self.gen.style(z_dev)
+        ws = self.walk([w] * self.gen.n_latent, alpha_dev, layers=layers)
+        latent = torch.stack(ws, 1) if not _is_block(ws) else ws[0]._base
+        return self.gen.synthesize(latent, noise=noise, want_uint8=want_uint8, want_float=not want_uint8)
+
+    @torch.no_grad()
+    def edit(self, z, alpha, layers=None, noise=None, sync=True) -> np.ndarray:
+        """``z``: [B, dim] host array / tensor (float64 from the numpy sampler is fine, it is cast to
+        float32 exactly like ``torch.Tensor(z)`` in train.py:56); ``alpha``: [B, A] host."""
+        self.z_host.copy_(torch.as_tensor(z).to(torch.float32))
+        self.alpha_host.copy_(torch.as_tensor(alpha).to(torch.float32).reshape(self.batch, -1))
+        self.z_dev.copy_(self.z_host, non_blocking=True)
+        self.alpha_dev.copy_(self.alpha_host, non_blocking=True)
+        u8 = self.edit_device(self.z_dev, self.alpha_dev, layers=layers, noise=noise, want_uint8=True)
+        self.out_host.copy_(u8, non_blocking=True)
+        if sync:
+            torch.cuda.current_stream(self.device).synchronize()
+        return self.out_host.numpy()
+
+
+def _is_block(ws) -> bool:
+    """True when the walk returned the unbound views of one contiguous [B, L, D] tensor, in order."""
+    base = getattr(ws[0], "_base", None)
+    if base is None or base.ndim != 3 or base.shape[1] != len(ws):
+        return False
+    return all(getattr(w, "_base", None) is base and w.data_ptr() == base[:, i].data_ptr() for i, w in enumerate(ws))
