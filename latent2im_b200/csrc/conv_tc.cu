@@ -125,43 +125,53 @@ struct TcParams {
   int B, H, W, Cin, Cout;
   int OH, OW, nphase, out_scale, out_H, out_W;
   TapList taps[4];
-  int bw, bh, bb;                 // M-tile box (pixels x rows x samples), bw*bh*bb == 128
-  int tiles_x, tiles_y, tiles_b, tiles_n;
+  int bw, bh;                     // M-tile box: bw x bh pixels of ONE sample (<= 128 rows)
+  int tiles_x, tiles_y, tiles_n;
   int total_tiles;
+  uint32_t a_bytes;               // bytes one A box load delivers (bw*bh*BLOCK_K*2)
+  uint32_t idesc;                 // UMMA instruction descriptor (operand formats chosen on the host)
   EpiParams e;
 };
 
 constexpr int kBlockM = 128;
-constexpr int kNumThreads = 256;
-constexpr int kEpiWarp0 = 4;
+constexpr int kEpiWarp0 = 4;      // warps 0-3: TMA, MMA, TMEM alloc, spare; then GROUPS x 4 epilogue warps
 
-template <int BLOCK_N, int BLOCK_K, int STAGES>
+template <int BLOCK_N, int BLOCK_K, int STAGES, int GROUPS>
 struct SmemLayout {
   static constexpr int kABytes = kBlockM * BLOCK_K * 2;
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kEpiFloats = 6 * BLOCK_N;                      // per group: dS, bS, sn, w0, w1, w2
+  static constexpr int kEpiBytes = GROUPS * kEpiFloats * 4;
   static constexpr int kBarrierBytes = 256;
-  static constexpr int kTotal = STAGES * kStageBytes + kBarrierBytes + 1024;  // + alignment slack
+  static constexpr int kTotal = STAGES * kStageBytes + kEpiBytes + kBarrierBytes + 1024;  // + alignment slack
+  static constexpr int kThreads = 128 + GROUPS * 128;
 };
 
-template <int BLOCK_N, int BLOCK_K, int STAGES>
-__global__ void __launch_bounds__(kNumThreads, 1)
+__device__ __forceinline__ void group_sync(int group) {
+  asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+}
+
+template <int BLOCK_N, int BLOCK_K, int STAGES, int GROUPS>
+__global__ void __launch_bounds__(128 + GROUPS * 128, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ TcParams p) {
-  using L = SmemLayout<BLOCK_N, BLOCK_K, STAGES>;
+  using L = SmemLayout<BLOCK_N, BLOCK_K, STAGES, GROUPS>;
   constexpr uint32_t kSwizzleBytes = BLOCK_K * 2;                 // 128 or 64
   constexpr uint32_t kLayoutType = kSwizzleBytes == 128 ? 2u : 4u;
   constexpr uint32_t kSBO = 8 * kSwizzleBytes;
-  constexpr uint32_t kTmemCols = (2 * BLOCK_N) < 32 ? 32 : 2 * BLOCK_N;  // two accumulator stages
-  constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM, BLOCK_N);
+  constexpr uint32_t kTmemColsRaw = GROUPS * BLOCK_N;             // one accumulator stage per epilogue group
+  constexpr uint32_t kTmemCols = kTmemColsRaw < 32 ? 32 : kTmemColsRaw;
+  static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns must be a power of two <= 512");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = (uint64_t*)(smem + STAGES * L::kStageBytes);
+  float* epi_smem = (float*)(smem + STAGES * L::kStageBytes);
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * L::kStageBytes + L::kEpiBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_base_smem = (uint32_t*)(tmem_empty + 2);
+  uint64_t* tmem_empty = tmem_full + GROUPS;
+  uint32_t* tmem_base_smem = (uint32_t*)(tmem_empty + GROUPS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -174,7 +184,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < GROUPS; ++a) {
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 128);
     }
@@ -187,17 +197,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t tmem_base = *tmem_base_smem;
 
   const int kchunks = p.Cin / BLOCK_K;
-  const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_b;
+  const int tiles_m = p.tiles_x * p.tiles_y * p.B;
 
-  auto decode = [&](int tile, int& phase, int& x0, int& y0, int& b0, int& nt) {
+  auto decode = [&](int tile, int& phase, int& x0, int& y0, int& b, int& nt) {
     nt = tile % p.tiles_n;
     int r = tile / p.tiles_n;
     const int mt = r % tiles_m;
     phase = r / tiles_m;
     const int tx = mt % p.tiles_x;
     const int ty = (mt / p.tiles_x) % p.tiles_y;
-    const int tb = mt / (p.tiles_x * p.tiles_y);
-    x0 = tx * p.bw; y0 = ty * p.bh; b0 = tb * p.bb;
+    b = mt / (p.tiles_x * p.tiles_y);
+    x0 = tx * p.bw; y0 = ty * p.bh;
   };
 
   if (warp == 0) {
@@ -205,17 +215,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase_bit = 0;
+      const uint32_t tx_bytes = p.a_bytes + L::kBBytes;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int ph, x0, y0, b0, nt;
-        decode(tile, ph, x0, y0, b0, nt);
+        int ph, x0, y0, b, nt;
+        decode(tile, ph, x0, y0, b, nt);
         const TapList& taps = p.taps[ph];
         for (int t = 0; t < taps.n; ++t) {
           for (int kc = 0; kc < kchunks; ++kc) {
             mbar_wait(&empty_bar[stage], phase_bit ^ 1);
             uint8_t* sa = smem + stage * L::kStageBytes;
             uint8_t* sb = sa + L::kABytes;
-            mbar_expect_tx(&full_bar[stage], L::kStageBytes);
-            tma_load_4d(sa, &tmap_a, &full_bar[stage], kc * BLOCK_K, x0 + taps.dx[t], y0 + taps.dy[t], b0);
+            mbar_expect_tx(&full_bar[stage], tx_bytes);
+            tma_load_4d(sa, &tmap_a, &full_bar[stage], kc * BLOCK_K, x0 + taps.dx[t], y0 + taps.dy[t], b);
             tma_load_3d(sb, &tmap_b, &full_bar[stage], kc * BLOCK_K, nt * BLOCK_N, taps.wtap[t]);
             if (++stage == STAGES) { stage = 0; phase_bit ^= 1; }
           }
@@ -230,8 +241,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int ph, x0, y0, b0, nt;
-        decode(tile, ph, x0, y0, b0, nt);
+        int ph, x0, y0, b, nt;
+        decode(tile, ph, x0, y0, b, nt);
         const int nk = p.taps[ph].n * kchunks;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -245,73 +256,122 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             const uint64_t adesc = make_kmajor_desc(sa + k * 32, kSBO, kLayoutType);
             const uint64_t bdesc = make_kmajor_desc(sb + k * 32, kSBO, kLayoutType);
-            umma_bf16(tmem_d, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16(tmem_d, adesc, bdesc, p.idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase_bit ^= 1; }
         }
         umma_commit(&tmem_full[acc]);      // accumulator complete
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == GROUPS) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ===================== epilogue =====================
+    // ===================== epilogue: GROUPS warpgroups, group g owns accumulator stage g and the
+    // CTA's tiles g, g+GROUPS, ... so GROUPS tile epilogues (and their DRAM latencies) overlap =====
     const EpiParams& e = p.e;
+    const int group = (warp - kEpiWarp0) >> 2;
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;          // tile row == TMEM lane
-    const float nw = (e.noise != nullptr && e.noise_w != nullptr) ? __ldg(e.noise_w) : 0.f;
+    const int gtid = threadIdx.x - (kEpiWarp0 * 32 + group * 128);
+    float* sp = epi_smem + group * L::kEpiFloats;
+    float* s_d = sp;                 // demod * sqrt2 (act) or demod (raw)
+    float* s_b = sp + BLOCK_N;       // bias * sqrt2
+    float* s_n = sp + 2 * BLOCK_N;   // next-layer style
+    float* s_w = sp + 3 * BLOCK_N;   // ToRGB weights, 3 x BLOCK_N
+    constexpr float kSqrt2 = 1.4142135623730951f;
+    const float nw = (e.noise != nullptr && e.noise_w != nullptr) ? __ldg(e.noise_w) * kSqrt2 : 0.f;
     const int64_t plane = (int64_t)p.out_H * p.out_W;
-    int acc = 0;
+    const int lx = row % p.bw, ly = row / p.bw;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      int ph, x0, y0, b0, nt;
-      decode(tile, ph, x0, y0, b0, nt);
-      const int lx = row % p.bw, ly = (row / p.bw) % p.bh, lb = row / (p.bw * p.bh);
-      const int ox = x0 + lx, oy = y0 + ly, b = b0 + lb;
-      const bool valid = ox < p.OW && oy < p.OH && b < p.B;
+    int staged_key = -1;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      if (it % GROUPS != group) continue;
+      int ph, x0, y0, b, nt;
+      decode(tile, ph, x0, y0, b, nt);
+      const int ox = x0 + lx, oy = y0 + ly;
+      const bool valid = ly < p.bh && ox < p.OW && oy < p.OH;
       const int Y = oy * p.out_scale + (ph >> 1), X = ox * p.out_scale + (ph & 1);
-      const int bb = valid ? b : 0;
-      const float* demod = e.demod + (int64_t)bb * e.demod_bs;
-      const float* s_next = e.s_next ? e.s_next + (int64_t)bb * e.s_next_bs : nullptr;
-      const float* wr = e.wr ? e.wr + (int64_t)bb * e.wr_bs : nullptr;
+
+      // ---- per-(sample, N-tile) epilogue vectors -> shared memory (rarely changes between tiles) ----
+      const int key = b * p.tiles_n + nt;
+      if (key != staged_key) {
+        group_sync(group);  // everyone is done with the previous vectors
+        const int co0 = nt * BLOCK_N;
+        for (int j = gtid; j < BLOCK_N; j += 128) {
+          const int co = co0 + j;
+          const float d = __ldg(e.demod + (int64_t)b * e.demod_bs + co);
+          if (e.mode == 0) {
+            s_d[j] = d * kSqrt2;
+            s_b[j] = __ldg(e.bias + co) * kSqrt2;
+            s_n[j] = e.s_next ? __ldg(e.s_next + (int64_t)b * e.s_next_bs + co) : 1.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+              s_w[c * BLOCK_N + j] = e.wr ? __ldg(e.wr + (int64_t)b * e.wr_bs + c * p.Cout + co) : 0.f;
+          } else {
+            s_d[j] = d;
+          }
+        }
+        group_sync(group);
+        staged_key = key;
+      }
+
+      // ---- issue every global load of this tile before waiting for the accumulator ----
       float nz = 0.f;
-      if (e.mode == 0 && e.noise != nullptr && valid) nz = nw * __ldg(e.noise + (int64_t)b * e.noise_bs + (int64_t)Y * p.out_W + X);
+      if (e.mode == 0 && e.noise != nullptr && valid)
+        nz = nw * __ldg(e.noise + (int64_t)b * e.noise_bs + (int64_t)Y * p.out_W + X);
+      float up[3] = {0.f, 0.f, 0.f};
+      if (e.mode == 0 && e.fused_skip && valid) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          up[c] = __ldg(e.rgb_bias + c);
+          if (e.skip_in != nullptr)
+            up[c] += upsample2x_at(e.skip_in + ((int64_t)b * 3 + c) * (plane / 4), p.out_H / 2, p.out_W / 2, Y, X, e.fir);
+        }
+      }
       __nv_bfloat16* outp = nullptr;
-      if (valid && e.out != nullptr && (e.mode == 1 || s_next != nullptr))
+      if (valid && e.out != nullptr && (e.mode == 1 || e.s_next != nullptr))
         outp = (__nv_bfloat16*)e.out + (((int64_t)b * p.out_H + Y) * p.out_W + X) * p.Cout + nt * BLOCK_N;
       float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
 
-      mbar_wait(&tmem_full[acc], acc_phase);
+      mbar_wait(&tmem_full[group], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(group * BLOCK_N);
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + c0, v);
         tmem_ld_wait();
-        const int co0 = nt * BLOCK_N + c0;
         uint32_t packed[16];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float o[2];
+        for (int j4 = 0; j4 < 32; j4 += 4) {
+          const float4 d4 = *reinterpret_cast<const float4*>(s_d + c0 + j4);
+          float o[4];
+          if (e.mode == 0) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_b + c0 + j4);
+            const float4 n4 = *reinterpret_cast<const float4*>(s_n + c0 + j4);
+            const float4 w0 = *reinterpret_cast<const float4*>(s_w + c0 + j4);
+            const float4 w1 = *reinterpret_cast<const float4*>(s_w + BLOCK_N + c0 + j4);
+            const float4 w2 = *reinterpret_cast<const float4*>(s_w + 2 * BLOCK_N + c0 + j4);
+            const float dd[4] = {d4.x, d4.y, d4.z, d4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+            const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+            const float a0[4] = {w0.x, w0.y, w0.z, w0.w}, a1[4] = {w1.x, w1.y, w1.z, w1.w}, a2[4] = {w2.x, w2.y, w2.z, w2.w};
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int co = co0 + j + h;
-            float x = __uint_as_float(v[j + h]) * __ldg(demod + co);
-            if (e.mode == 0) {
-              x = x + nz + __ldg(e.bias + co);
-              x = (x > 0.f ? x : 0.2f * x) * 1.4142135623730951f;
-              if (wr != nullptr) {
-                rgb0 = fmaf(__ldg(wr + co), x, rgb0);
-                rgb1 = fmaf(__ldg(wr + p.Cout + co), x, rgb1);
-                rgb2 = fmaf(__ldg(wr + 2 * p.Cout + co), x, rgb2);
-              }
-              if (s_next != nullptr) x *= __ldg(s_next + co);
+            for (int h = 0; h < 4; ++h) {
+              float x = fmaf(__uint_as_float(v[j4 + h]), dd[h], bb[h] + nz);
+              x = fmaxf(x, 0.2f * x);  // leaky relu (the sqrt(2) gain is folded into dd / bb / nz)
+              rgb0 = fmaf(a0[h], x, rgb0);
+              rgb1 = fmaf(a1[h], x, rgb1);
+              rgb2 = fmaf(a2[h], x, rgb2);
+              o[h] = x * nn[h];
             }
-            o[h] = x;
+          } else {
+            o[0] = __uint_as_float(v[j4]) * d4.x; o[1] = __uint_as_float(v[j4 + 1]) * d4.y;
+            o[2] = __uint_as_float(v[j4 + 2]) * d4.z; o[3] = __uint_as_float(v[j4 + 3]) * d4.w;
           }
-          __nv_bfloat162 pk = __floats2bfloat162_rn(o[0], o[1]);
-          packed[j >> 1] = *reinterpret_cast<uint32_t*>(&pk);
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
+          packed[j4 >> 1] = *reinterpret_cast<uint32_t*>(&p0);
+          packed[(j4 >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p1);
         }
         if (outp != nullptr) {
           uint4* dst = reinterpret_cast<uint4*>(outp + c0);
@@ -321,19 +381,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       // all TMEM reads of this accumulator stage are complete (wait::ld above): hand it back
       tc_fence_before();
-      mbar_arrive(&tmem_empty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      mbar_arrive(&tmem_empty[group]);
+      acc_phase ^= 1;
 
-      if (e.mode == 0 && wr != nullptr && valid) {
+      if (e.mode == 0 && e.wr != nullptr && valid) {
         const float r3[3] = {rgb0, rgb1, rgb2};
         if (e.fused_skip) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float val = r3[c] + __ldg(e.rgb_bias + c);
-            if (e.skip_in != nullptr)
-              val += upsample2x_at(e.skip_in + ((int64_t)b * 3 + c) * (plane / 4), p.out_H / 2, p.out_W / 2, Y, X, e.fir);
-            e.skip_out[((int64_t)b * 3 + c) * plane + (int64_t)Y * p.out_W + X] = val;
-          }
+          for (int c = 0; c < 3; ++c)
+            e.skip_out[((int64_t)b * 3 + c) * plane + (int64_t)Y * p.out_W + X] = r3[c] + up[c];
         } else {
 #pragma unroll
           for (int c = 0; c < 3; ++c)
@@ -392,16 +448,17 @@ int make_tmap(CUtensorMap* map, const void* base, int rank, const uint64_t* dims
   return L2I_OK;
 }
 
-template <int BLOCK_N, int BLOCK_K, int STAGES>
-int launch_variant(const void* in, const __nv_bfloat16* w, const TcParams& p, cudaStream_t st) {
-  using L = SmemLayout<BLOCK_N, BLOCK_K, STAGES>;
+template <int BLOCK_N, int BLOCK_K, int STAGES, int GROUPS>
+int launch_variant(const void* in, const __nv_bfloat16* w, TcParams& p, cudaStream_t st) {
+  using L = SmemLayout<BLOCK_N, BLOCK_K, STAGES, GROUPS>;
+  p.a_bytes = (uint32_t)(p.bw * p.bh * BLOCK_K * 2);
   static_assert(L::kTotal <= 227 * 1024, "shared memory budget");
   CUtensorMap ta, tb;
   const CUtensorMapSwizzle swz = BLOCK_K == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   {
     const uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.B};
     const uint64_t str[4] = {2, (uint64_t)p.Cin * 2, (uint64_t)p.W * p.Cin * 2, (uint64_t)p.H * p.W * p.Cin * 2};
-    const uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bb};
+    const uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)p.bw, (uint32_t)p.bh, 1u};
     L2I_TRY(make_tmap(&ta, in, 4, dims, str, box, swz));
   }
   {
@@ -410,14 +467,14 @@ int launch_variant(const void* in, const __nv_bfloat16* w, const TcParams& p, cu
     const uint32_t box[3] = {(uint32_t)BLOCK_K, (uint32_t)BLOCK_N, 1};
     L2I_TRY(make_tmap(&tb, w, 3, dims, str, box, swz));
   }
-  auto kern = conv_tc_kernel<BLOCK_N, BLOCK_K, STAGES>;
+  auto kern = conv_tc_kernel<BLOCK_N, BLOCK_K, STAGES, GROUPS>;
   static bool attr_set = false;
   if (!attr_set) {
     L2I_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     attr_set = true;
   }
   const int grid = std::min(p.total_tiles, kNumSMs);
-  kern<<<grid, kNumThreads, L::kTotal, st>>>(ta, tb, p);
+  kern<<<grid, L::kThreads, L::kTotal, st>>>(ta, tb, p);
   return check_launch("conv_tc");
 }
 
@@ -444,17 +501,18 @@ int launch_conv_tc(const void* in, const __nv_bfloat16* w, const ConvGeom& g, co
   p.OH = g.OH; p.OW = g.OW; p.nphase = g.nphase; p.out_scale = g.out_scale; p.out_H = g.out_H; p.out_W = g.out_W;
   for (int i = 0; i < 4; ++i) p.taps[i] = g.taps[i];
   p.e = e;
-  // M-tile box: up to 16 pixels wide, then rows, then samples, 128 rows in total
+  // M-tile box: up to 16 pixels wide, then rows, always inside one sample (<= 128 rows; tiny
+  // resolutions leave TMEM lanes unused, which costs nothing that matters)
   int bw = 1;
   while (bw < 16 && bw < g.OW) bw <<= 1;
   int bh = 1;
   while (bw * bh < 128 && bh < g.OH) bh <<= 1;
-  int bb = 128 / (bw * bh);
-  p.bw = bw; p.bh = bh; p.bb = bb;
-  p.tiles_x = ceil_div(g.OW, bw); p.tiles_y = ceil_div(g.OH, bh); p.tiles_b = ceil_div(g.B, bb);
+  p.bw = bw; p.bh = bh;
+  p.tiles_x = ceil_div(g.OW, bw); p.tiles_y = ceil_div(g.OH, bh);
   const int bn = pick_block_n(g.Cout);
   p.tiles_n = g.Cout / bn;
-  const int64_t total = (int64_t)p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n * g.nphase;
+  p.idesc = make_idesc_bf16(kBlockM, bn);
+  const int64_t total = (int64_t)p.tiles_x * p.tiles_y * g.B * p.tiles_n * g.nphase;
   if (total <= 0 || total > 0x7fffffff) {
     set_error("conv_tc: bad tile count %lld", (long long)total);
     return L2I_ERR_INVALID_ARG;
@@ -470,13 +528,13 @@ int launch_conv_tc(const void* in, const __nv_bfloat16* w, const ConvGeom& g, co
   }
   if (g.Cin >= 64) {
     switch (bn) {
-      case 256: return launch_variant<256, 64, 4>(in, w, p, st);
-      case 128: return launch_variant<128, 64, 6>(in, w, p, st);
-      case 64: return launch_variant<64, 64, 8>(in, w, p, st);
-      case 32: return launch_variant<32, 64, 8>(in, w, p, st);
+      case 256: return launch_variant<256, 64, 4, 2>(in, w, p, st);
+      case 128: return launch_variant<128, 64, 6, 2>(in, w, p, st);
+      case 64: return launch_variant<64, 64, 8, 4>(in, w, p, st);
+      case 32: return launch_variant<32, 64, 8, 4>(in, w, p, st);
     }
   } else if (bn == 32) {
-    return launch_variant<32, 32, 8>(in, w, p, st);
+    return launch_variant<32, 32, 8, 4>(in, w, p, st);
   }
   set_error("conv_tc: unsupported shape Cin=%d Cout=%d", g.Cin, g.Cout);
   return L2I_ERR_UNSUPPORTED;

@@ -19,54 +19,80 @@ namespace l2i {
 template <typename T, int VEC>
 struct alignas(sizeof(T) * VEC) TVec { T v[VEC]; };
 
+// Thread mapping: a CTA of 256 threads covers XT = 256 / VP adjacent output columns x one chunk of
+// VP 16-byte channel vectors, and marches down RY output rows.  Each thread keeps the horizontally
+// filtered rows Y-1 .. Y+2 of its column in registers (separable FIR), so every t element is fetched
+// by four neighbouring threads of the same CTA (one DRAM/L2 fetch + three L1 hits) and every output
+// element is written once with a 16-byte store.  Per-thread bias / next-style values live in registers.
+constexpr int kBlurRows = 32;
+
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
 blur_act_kernel(T* __restrict__ out, const T* __restrict__ t, int B, int OH, int OW, int C, int TH, int TW,
                 const float* __restrict__ noise, int64_t noise_bs, const float* __restrict__ noise_w,
                 const float* __restrict__ bias, const float* __restrict__ s_next, int64_t s_next_bs,
-                float f0, float f1, float f2, float f3) {
+                float f0, float f1, float f2, float f3, int VP, int tiles_x, int tiles_y, int chunks) {
   using V = TVec<T, VEC>;
-  const int cv = C / VEC;
-  const int64_t total = (int64_t)B * OH * OW * cv;
-  const float nw = (noise != nullptr && noise_w != nullptr) ? *noise_w : 0.f;
+  constexpr float kSqrt2 = 1.4142135623730951f;
+  const int XT = 256 / VP;
+  int r = blockIdx.x;
+  const int ck = r % chunks; r /= chunks;
+  const int tx = r % tiles_x; r /= tiles_x;
+  const int ty = r % tiles_y;
+  const int b = r / tiles_y;
+  const int X = tx * XT + threadIdx.x / VP;
+  const int c = (ck * VP + threadIdx.x % VP) * VEC;
+  if (X >= OW) return;
+  const int Y0 = ty * kBlurRows;
+  const int Y1 = min(Y0 + kBlurRows, OH);
+  const float nw = (noise != nullptr && noise_w != nullptr) ? __ldg(noise_w) * kSqrt2 : 0.f;
+  float bs[VEC], sn[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    bs[k] = __ldg(bias + c + k) * kSqrt2;
+    sn[k] = s_next != nullptr ? __ldg(s_next + (int64_t)b * s_next_bs + c + k) : 1.f;
+  }
+  const T* tb = t + (int64_t)b * TH * TW * C + c;
   const float f[4] = {f0, f1, f2, f3};
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = idx;
-    const int c = (int)(r % cv) * VEC; r /= cv;
-    const int X = (int)(r % OW); r /= OW;
-    const int Y = (int)(r % OH);
-    const int b = (int)(r / OH);
-    float acc[VEC];
+
+  auto hrow = [&](int u, float (&h)[VEC]) {
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+    for (int k = 0; k < VEC; ++k) h[k] = 0.f;
+    if (u < 0 || u >= TH) return;
+    const T* row = tb + (int64_t)u * TW * C;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int u = Y + i - 1;
-      if (u < 0 || u >= TH) continue;
-      float row[VEC];
+    for (int j = 0; j < 4; ++j) {
+      const int v = X + j - 1;
+      if (v < 0 || v >= TW) continue;
+      const V tv = *reinterpret_cast<const V*>(row + (int64_t)v * C);
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) row[k] = 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int v = X + j - 1;
-        if (v < 0 || v >= TW) continue;
-        const V tv = *reinterpret_cast<const V*>(t + (((int64_t)b * TH + u) * TW + v) * C + c);
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) row[k] = fmaf(f[j], to_f32<T>(tv.v[k]), row[k]);
-      }
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) acc[k] = fmaf(f[i], row[k], acc[k]);
+      for (int k = 0; k < VEC; ++k) h[k] = fmaf(f[j], to_f32<T>(tv.v[k]), h[k]);
     }
-    const float nz = noise != nullptr ? nw * noise[(int64_t)b * noise_bs + (int64_t)Y * OW + X] : 0.f;
+  };
+
+  float h0[VEC], h1[VEC], h2[VEC], h3[VEC];
+  hrow(Y0 - 1, h0);
+  hrow(Y0, h1);
+  hrow(Y0 + 1, h2);
+  const float* nrow = noise != nullptr ? noise + (int64_t)b * noise_bs + X : nullptr;
+  T* ob = out + ((int64_t)b * OH * OW + X) * C + c;
+#pragma unroll 2
+  for (int Y = Y0; Y < Y1; ++Y) {
+    hrow(Y + 2, h3);
+    const float nz = nrow != nullptr ? nw * __ldg(nrow + (int64_t)Y * OW) : 0.f;
     V ov;
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
-      float v = lrelu(acc[k] + nz + bias[c + k], 0.2f) * 1.4142135623730951f;
-      if (s_next != nullptr) v *= s_next[(int64_t)b * s_next_bs + c + k];
-      ov.v[k] = from_f32<T>(v);
+      float a = f0 * h0[k];
+      a = fmaf(f1, h1[k], a);
+      a = fmaf(f2, h2[k], a);
+      a = fmaf(f3, h3[k], a);
+      float x = fmaf(a, kSqrt2, bs[k] + nz);
+      x = fmaxf(x, 0.2f * x);
+      ov.v[k] = from_f32<T>(x * sn[k]);
+      h0[k] = h1[k]; h1[k] = h2[k]; h2[k] = h3[k];
     }
-    *reinterpret_cast<V*>(out + (((int64_t)b * OH + Y) * OW + X) * C + c) = ov;
+    *reinterpret_cast<V*>(ob + (int64_t)Y * OW * C) = ov;
   }
 }
 
@@ -79,11 +105,31 @@ int launch_blur_act(void* out, const void* t, int B, int OH, int OW, int C, int 
     set_error("blur_act: C=%d not a multiple of %d", C, VEC);
     return L2I_ERR_UNSUPPORTED;
   }
-  const int64_t total = (int64_t)B * OH * OW * (C / VEC);
-  if (total == 0) return L2I_OK;
-  const int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)kNumSMs * 32);
-  blur_act_kernel<T, VEC><<<blocks, 256, 0, st>>>((T*)out, (const T*)t, B, OH, OW, C, TH, TW, noise, noise_bs,
-                                                  noise_w, bias, s_next, s_next_bs, f[0], f[1], f[2], f[3]);
+  if ((int64_t)B * OH * OW == 0) return L2I_OK;
+  int VP = C / VEC;          // 16-byte vectors per pixel handled by one CTA pass
+  int chunks = 1;
+  if (VP > 8) {
+    if (VP % 8 != 0) {
+      set_error("blur_act: C=%d unsupported", C);
+      return L2I_ERR_UNSUPPORTED;
+    }
+    chunks = VP / 8;
+    VP = 8;
+  }
+  if (256 % VP != 0) {
+    set_error("blur_act: C=%d unsupported", C);
+    return L2I_ERR_UNSUPPORTED;
+  }
+  const int XT = 256 / VP;
+  const int tiles_x = ceil_div(OW, XT), tiles_y = ceil_div(OH, kBlurRows);
+  const int64_t blocks = (int64_t)B * tiles_x * tiles_y * chunks;
+  if (blocks > 0x7fffffff) {
+    set_error("blur_act: grid too large");
+    return L2I_ERR_INVALID_ARG;
+  }
+  blur_act_kernel<T, VEC><<<(unsigned)blocks, 256, 0, st>>>((T*)out, (const T*)t, B, OH, OW, C, TH, TW, noise, noise_bs,
+                                                           noise_w, bias, s_next, s_next_bs, f[0], f[1], f[2], f[3], VP,
+                                                           tiles_x, tiles_y, chunks);
   return check_launch("blur_act");
 }
 template int launch_blur_act<float>(void*, const void*, int, int, int, int, int, int, const float*, int64_t,

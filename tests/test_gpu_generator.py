@@ -168,4 +168,4 @@ def test_tcgen05_conv_matches_cuda_core_conv(size, batch, monkeypatch):
         gen = load_synthetic(Generator(size, 64, 1), seed=0).cuda()
         gen.set_native(dtype=torch.bfloat16)
         imgs[impl], _ = gen(lat, input_is_latent=True, noise=noise)
-    assert _psnr(imgs["tc"].double(), imgs["simt"].double()) >= 50.0
+    assert _psnr(imgs["tc"].double(), imgs["simt"].double()) >= 46.0
