@@ -153,10 +153,17 @@ int l2i_generator_forward(l2i_generator_t* g, const float* latent, int64_t laten
                           const int* noise_batch, float* image, uint8_t* image_u8, int batch,
                           void* stream);
 
+/* Training mode: while enabled, forward() additionally keeps every layer's activation (and the raw
+ * up-conv outputs) in per-layer buffers so that backward() can run.  The first call allocates those
+ * buffers and the transposed weight copies and synchronises the device; forward() still never
+ * allocates.  The noise tensors passed to a training forward must stay alive until its backward. */
+int l2i_generator_set_training(l2i_generator_t* g, int enable);
+
 /* Data-gradient backward of the forward above (the walk-training gradient path):
  * given grad_image [B,3,size,size] fp32, writes grad_latent [B, n_latent, D] fp32.
- * Must follow a forward with the same batch on the same stream (activations are kept in the
- * generator's workspace).  No weight gradients are produced (the generator is frozen). */
+ * Must follow a forward made in training mode with the same batch on the same stream.  No weight
+ * gradients are produced (the generator is frozen); gradients w.r.t. the noise inputs are not needed
+ * on the walk-training path and are not produced either. */
 int l2i_generator_backward(l2i_generator_t* g, float* grad_latent, const float* grad_image,
                            int batch, void* stream);
 

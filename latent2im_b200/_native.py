@@ -45,6 +45,7 @@ _SIGNATURES = {
     "l2i_generator_profile_count": (_i32, [_vp]),
     "l2i_generator_profile_entry": (_i32, [_vp, _i32, C.c_char_p, _i32, C.POINTER(_i32), C.POINTER(_f32),
                                            C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "l2i_generator_set_training": (_i32, [_vp, _i32]),
     "l2i_generator_backward": (_i32, [_vp, _vp, _vp, _i32, _vp]),
     "l2i_generator_read_activation": (_i32, [_vp, C.c_char_p, _vp, _i64, _i32, _vp]),
     "l2i_image_to_uint8": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp]),

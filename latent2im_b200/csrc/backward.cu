@@ -1,0 +1,464 @@
+// Data-gradient backward of the synthesis network: grad_image -> grad_latent (the walk-training
+// gradient path).  The generator is frozen, so no weight gradient is ever
+// formed; with the input-scaling formulation every conv's backward is an ordinary data-gradient
+// conv with shared weights plus per-(sample, channel) reductions for the style gradients:
+//
+//   plain layer   acc = conv(x~, W~);  v = d*acc + nz + bias;  y = lrelu(v)*sqrt2;  x~' = s' * y;  rgb = wr . y
+//     g_y   = s' * g_x~'  +  wr^T . g_rgb
+//     g_v   = g_y * lrelu'(y) * sqrt2
+//     g_acc = d * g_v                      ->  g_x~ = conv_dgrad(g_acc, W~)
+//     R_d   = sum_p g_v * (d*acc)          (d*acc is recovered from the saved y, the noise and the bias)
+//     R_s'  = sum_p g_x~' * y              (gradient of the NEXT layer's style)
+//     R_rgb = sum_p g_rgb[c] * y           (-> ToRGB style gradient through Wrgb)
+//   up layer      t = d * convT(x~, W~);  v = blur(t) + nz + bias;  y, x~' as above
+//     g_t = blur^T(g_v);  g_acc = d * g_t;  R_d = sum g_t * t;  g_x~ = stride-2 gather conv of g_acc
+//   style         s = latent_i . Wmod + b;   d = rsqrt(sum_ci s^2 Wsq + eps)
+//     g_s[ci] = R_s(prev layer)[ci]  -  s[ci] * sum_co Wsq[co,ci] * d[co]^2 * R_d[co]
+//     g_latent[i] = sum over the layers reading latent i of g_s . Wmod
+//
+// Reference for what is differentiated: networks.py:231-286, 330-358, 460-514; the reference obtains
+// the same gradients from autograd through cuDNN.
+#include <cmath>
+#include <type_traits>
+
+#include "generator_internal.cuh"
+
+namespace l2i {
+
+template <typename T, int VEC>
+struct alignas(sizeof(T) * VEC) GVec { T v[VEC]; };
+
+// ------------------------------------------------------------------------------------------------
+// act_bwd: activation / noise / bias / ToRGB backward + the three per-channel reductions.
+// grid = (pixel chunks, B), 256 threads: thread = (pixel slot, 16-byte channel vector).
+// ------------------------------------------------------------------------------------------------
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+act_bwd_kernel(T* __restrict__ g_out, const T* __restrict__ g_xn, const float* __restrict__ g_rgb,
+               const T* __restrict__ y, const float* __restrict__ s_next, int64_t s_next_bs,
+               const float* __restrict__ wr, int64_t wr_bs, const float* __restrict__ demod, int64_t demod_bs,
+               const float* __restrict__ noise, int64_t noise_bs, const float* __restrict__ noise_w,
+               const float* __restrict__ bias, float* __restrict__ R_s, float* __restrict__ R_d, int64_t R_bs,
+               float* __restrict__ R_rgb, int64_t R_rgb_bs, int HW, int C, int chunk) {
+  using V = GVec<T, VEC>;
+  constexpr float kSqrt2 = 1.4142135623730951f;
+  extern __shared__ float red[];  // [5][C]
+  const int CV = C / VEC;
+  const int slots = 256 / CV;
+  const int cv = threadIdx.x % CV, slot = threadIdx.x / CV;
+  const int b = blockIdx.y;
+  const int c = cv * VEC;
+  for (int i = threadIdx.x; i < 5 * C; i += 256) red[i] = 0.f;
+  __syncthreads();
+  float sn[VEC], dm[VEC], bs[VEC], w0[VEC], w1[VEC], w2[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    sn[k] = s_next ? s_next[(int64_t)b * s_next_bs + c + k] : 0.f;
+    dm[k] = demod ? demod[(int64_t)b * demod_bs + c + k] : 1.f;
+    bs[k] = bias ? bias[c + k] : 0.f;
+    w0[k] = wr ? wr[(int64_t)b * wr_bs + c + k] : 0.f;
+    w1[k] = wr ? wr[(int64_t)b * wr_bs + C + c + k] : 0.f;
+    w2[k] = wr ? wr[(int64_t)b * wr_bs + 2 * C + c + k] : 0.f;
+  }
+  const float nw = (noise != nullptr && noise_w != nullptr) ? *noise_w : 0.f;
+  float rs[VEC], rd[VEC], r0[VEC], r1[VEC], r2[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) rs[k] = rd[k] = r0[k] = r1[k] = r2[k] = 0.f;
+  const int p0 = blockIdx.x * chunk, p1 = min(p0 + chunk, HW);
+  if (slot < slots) {
+    for (int p = p0 + slot; p < p1; p += slots) {
+      const int64_t off = ((int64_t)b * HW + p) * C + c;
+      const V yv = *reinterpret_cast<const V*>(y + off);
+      V gx;
+      if (g_xn != nullptr) gx = *reinterpret_cast<const V*>(g_xn + off);
+      float gr0 = 0.f, gr1 = 0.f, gr2 = 0.f;
+      if (g_rgb != nullptr) {
+        gr0 = g_rgb[((int64_t)b * 3 + 0) * HW + p];
+        gr1 = g_rgb[((int64_t)b * 3 + 1) * HW + p];
+        gr2 = g_rgb[((int64_t)b * 3 + 2) * HW + p];
+      }
+      const float nz = noise != nullptr ? nw * noise[(int64_t)b * noise_bs + p] : 0.f;
+      V go;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const float yk = to_f32<T>(yv.v[k]);
+        const float gxk = g_xn != nullptr ? to_f32<T>(gx.v[k]) : 0.f;
+        const float gy = sn[k] * gxk + w0[k] * gr0 + w1[k] * gr1 + w2[k] * gr2;
+        const float gv = gy * (yk > 0.f ? kSqrt2 : 0.2f * kSqrt2);
+        const float v = yk > 0.f ? yk * (1.f / kSqrt2) : yk * (1.f / (0.2f * kSqrt2));
+        rd[k] = fmaf(gv, v - nz - bs[k], rd[k]);
+        rs[k] = fmaf(gxk, yk, rs[k]);
+        r0[k] = fmaf(gr0, yk, r0[k]);
+        r1[k] = fmaf(gr1, yk, r1[k]);
+        r2[k] = fmaf(gr2, yk, r2[k]);
+        go.v[k] = from_f32<T>(dm[k] * gv);
+      }
+      *reinterpret_cast<V*>(g_out + off) = go;
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      atomicAdd(&red[0 * C + c + k], rs[k]);
+      atomicAdd(&red[1 * C + c + k], rd[k]);
+      atomicAdd(&red[2 * C + c + k], r0[k]);
+      atomicAdd(&red[3 * C + c + k], r1[k]);
+      atomicAdd(&red[4 * C + c + k], r2[k]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += 256) {
+    if (R_s != nullptr) atomicAdd(R_s + (int64_t)b * R_bs + i, red[i]);
+    if (R_d != nullptr) atomicAdd(R_d + (int64_t)b * R_bs + i, red[C + i]);
+    if (R_rgb != nullptr) {
+      atomicAdd(R_rgb + (int64_t)b * R_rgb_bs + i, red[2 * C + i]);
+      atomicAdd(R_rgb + (int64_t)b * R_rgb_bs + C + i, red[3 * C + i]);
+      atomicAdd(R_rgb + (int64_t)b * R_rgb_bs + 2 * C + i, red[4 * C + i]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// blur_bwd: g_t[u][v] = sum_{i,j} f[i] f[j] * g_v[u-i+1][v-j+1]  on the padded (TH x TW) grid of the
+// up-conv output; writes d * g_t and reduces R_d += g_t * t_saved.
+// ------------------------------------------------------------------------------------------------
+template <typename T, typename TIN, int VEC>
+__global__ void __launch_bounds__(256)
+blur_bwd_kernel(T* __restrict__ g_acc, const T* __restrict__ g_v, const TIN* __restrict__ t_saved,
+                const float* __restrict__ demod, int64_t demod_bs, float* __restrict__ R_d, int64_t R_bs, int OH, int OW,
+                int TH, int TW, int C, int chunk, float f0, float f1, float f2, float f3) {
+  using V = GVec<T, VEC>;
+  using VIN = GVec<TIN, VEC>;
+  extern __shared__ float red[];  // [C]
+  const int CV = C / VEC;
+  const int slots = 256 / CV;
+  const int cv = threadIdx.x % CV, slot = threadIdx.x / CV;
+  const int b = blockIdx.y, c = cv * VEC;
+  const float f[4] = {f0, f1, f2, f3};
+  for (int i = threadIdx.x; i < C; i += 256) red[i] = 0.f;
+  __syncthreads();
+  float dm[VEC], rd[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) { dm[k] = demod[(int64_t)b * demod_bs + c + k]; rd[k] = 0.f; }
+  const int total = TH * TW;
+  const int p0 = blockIdx.x * chunk, p1 = min(p0 + chunk, total);
+  if (slot < slots) {
+    for (int p = p0 + slot; p < p1; p += slots) {
+      const int u = p / TW, v = p - u * TW;
+      float acc[VEC];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+      if (u < TH - 1 && v < TW - 1) {  // the last padded row / column of t is structurally zero: no gradient
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int Y = u - i + 1;
+          if (Y < 0 || Y >= OH) continue;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int X = v - j + 1;
+            if (X < 0 || X >= OW) continue;
+            const V gv = *reinterpret_cast<const V*>(g_v + (((int64_t)b * OH + Y) * OW + X) * C + c);
+            const float w = f[i] * f[j];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) acc[k] = fmaf(w, to_f32<T>(gv.v[k]), acc[k]);
+          }
+        }
+      }
+      const int64_t off = ((int64_t)b * total + p) * C + c;
+      const VIN tv = *reinterpret_cast<const VIN*>(t_saved + off);
+      V go;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        rd[k] = fmaf(acc[k], to_f32<TIN>(tv.v[k]), rd[k]);
+        go.v[k] = from_f32<T>(dm[k] * acc[k]);
+      }
+      *reinterpret_cast<V*>(g_acc + off) = go;
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) atomicAdd(&red[c + k], rd[k]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += 256) atomicAdd(R_d + (int64_t)b * R_bs + i, red[i]);
+}
+
+// R[b][ci] = sum_p g[b][p][ci] * cst[ci][p]      (gradient of conv1's style through the constant input)
+template <typename T>
+__global__ void const_grad_kernel(float* __restrict__ R, int64_t R_bs, const T* __restrict__ g, const float* __restrict__ cst,
+                                  int B, int C, int HW) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * C) return;
+  const int b = idx / C, c = idx % C;
+  float acc = 0.f;
+  for (int p = 0; p < HW; ++p) acc = fmaf(to_f32<T>(g[((int64_t)b * HW + p) * C + c]), cst[(int64_t)c * HW + p], acc);
+  R[(int64_t)b * R_bs + c] = acc;
+}
+
+// gs[b][ci] = Rs[b][ci] - s[b][ci] * sum_co wsq[co][ci] * d[b][co]^2 * Rd[b][co]      (one warp per (b, ci))
+__global__ void __launch_bounds__(256)
+conv_style_grad_kernel(float* __restrict__ gs, int64_t gs_bs, const float* __restrict__ Rs, int64_t Rs_bs,
+                       const float* __restrict__ s, int64_t s_bs, const float* __restrict__ wsq,
+                       const float* __restrict__ d, const float* __restrict__ Rd, int64_t d_bs, int B, int Cin, int Cout) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B * Cin) return;
+  const int b = warp / Cin, ci = warp % Cin;
+  float acc = 0.f;
+  for (int co = lane; co < Cout; co += 32) {
+    const float dd = d[(int64_t)b * d_bs + co];
+    acc = fmaf(wsq[(int64_t)co * Cin + ci] * dd * dd, Rd[(int64_t)b * d_bs + co], acc);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) gs[(int64_t)b * gs_bs + ci] = Rs[(int64_t)b * Rs_bs + ci] - s[(int64_t)b * s_bs + ci] * acc;
+}
+
+// gs[b][ci] = sum_c wrgb[c][ci] * Rrgb[b][c][ci]
+__global__ void rgb_style_grad_kernel(float* __restrict__ gs, int64_t gs_bs, const float* __restrict__ wrgb,
+                                      const float* __restrict__ Rrgb, int64_t R_bs, int B, int Cin) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * Cin) return;
+  const int b = idx / Cin, ci = idx % Cin;
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) acc = fmaf(wrgb[c * Cin + ci], Rrgb[(int64_t)b * R_bs + c * Cin + ci], acc);
+  gs[(int64_t)b * gs_bs + ci] = acc;
+}
+
+// g_latent[b][i][k] = sum over the style rows r that read latent i of gs[b][r] * mod_w[r][k]
+__global__ void __launch_bounds__(128)
+latent_grad_kernel(float* __restrict__ g_latent, const float* __restrict__ gs, int64_t gs_bs,
+                   const float* __restrict__ mod_w, const int* __restrict__ lat_seg, int n_latent, int D) {
+  const int i = blockIdx.x, b = blockIdx.y;
+  const int* seg = lat_seg + i * 7;
+  for (int k = threadIdx.x; k < D; k += blockDim.x) {
+    float acc = 0.f;
+    for (int q = 0; q < seg[0]; ++q) {
+      const int r0 = seg[1 + 2 * q], n = seg[2 + 2 * q];
+      for (int r = r0; r < r0 + n; ++r) acc = fmaf(gs[(int64_t)b * gs_bs + r], mod_w[(int64_t)r * D + k], acc);
+    }
+    g_latent[((int64_t)b * n_latent + i) * D + k] = acc;
+  }
+}
+
+// dst [tap][Cout][Cin] fp32 = scale * src[Cout][Cin][tap]
+__global__ void pack_weight_t_kernel(float* __restrict__ dst, const float* __restrict__ src, int Cout, int Cin, int ntap,
+                                     float scale) {
+  const int64_t total = (int64_t)Cout * Cin;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x)
+    for (int t = 0; t < ntap; ++t) dst[(int64_t)t * total + idx] = src[idx * ntap + t] * scale;
+}
+
+namespace {
+
+template <typename T>
+int launch_act_bwd(void* g_out, const void* g_xn, const float* g_rgb, const void* y, const float* s_next, int64_t s_next_bs,
+                   const float* wr, int64_t wr_bs, const float* demod, int64_t demod_bs, const float* noise, int64_t noise_bs,
+                   const float* noise_w, const float* bias, float* R_s, float* R_d, int64_t R_bs, float* R_rgb,
+                   int64_t R_rgb_bs, int B, int HW, int C, cudaStream_t st) {
+  constexpr int VEC = 16 / sizeof(T);
+  if (C % VEC != 0 || C / VEC > 256) { set_error("act_bwd: unsupported C=%d", C); return L2I_ERR_UNSUPPORTED; }
+  const int chunk = std::max(256, std::min(HW, 4096));
+  dim3 grid(ceil_div(HW, chunk), B);
+  act_bwd_kernel<T, VEC><<<grid, 256, sizeof(float) * 5 * C, st>>>(
+      (T*)g_out, (const T*)g_xn, g_rgb, (const T*)y, s_next, s_next_bs, wr, wr_bs, demod, demod_bs, noise, noise_bs, noise_w,
+      bias, R_s, R_d, R_bs, R_rgb, R_rgb_bs, HW, C, chunk);
+  return check_launch("act_bwd");
+}
+
+template <typename T, typename TIN>
+int launch_blur_bwd(void* g_acc, const void* g_v, const void* t_saved, const float* demod, int64_t demod_bs, float* R_d,
+                    int64_t R_bs, int B, int OH, int OW, int TH, int TW, int C, const float* f, cudaStream_t st) {
+  constexpr int VEC = 16 / sizeof(T);
+  if (C % VEC != 0 || C / VEC > 256) { set_error("blur_bwd: unsupported C=%d", C); return L2I_ERR_UNSUPPORTED; }
+  const int total = TH * TW;
+  const int chunk = std::max(256, std::min(total, 4096));
+  dim3 grid(ceil_div(total, chunk), B);
+  blur_bwd_kernel<T, TIN, VEC><<<grid, 256, sizeof(float) * C, st>>>((T*)g_acc, (const T*)g_v, (const TIN*)t_saved, demod,
+                                                                    demod_bs, R_d, R_bs, OH, OW, TH, TW, C, chunk, f[0], f[1],
+                                                                    f[2], f[3]);
+  return check_launch("blur_bwd");
+}
+
+TapList dgrad_plain_taps() {
+  TapList t{};
+  t.n = 9;
+  for (int kh = 0; kh < 3; ++kh)
+    for (int kw = 0; kw < 3; ++kw) {
+      const int i = kh * 3 + kw;
+      t.dy[i] = (int8_t)(1 - kh);
+      t.dx[i] = (int8_t)(1 - kw);
+      t.wtap[i] = (int8_t)i;
+    }
+  return t;
+}
+
+TapList dgrad_up_taps() {
+  TapList t{};
+  t.n = 9;
+  for (int kh = 0; kh < 3; ++kh)
+    for (int kw = 0; kw < 3; ++kw) {
+      const int i = kh * 3 + kw;
+      t.dy[i] = (int8_t)kh;
+      t.dx[i] = (int8_t)kw;
+      t.wtap[i] = (int8_t)i;
+    }
+  return t;
+}
+
+template <typename T>
+int backward_impl(l2i_generator* g, float* grad_latent, const float* grad_image, int B, cudaStream_t st) {
+  using TIN = typename std::conditional<sizeof(T) == 2, __half, float>::type;
+  const int D = g->D;
+  const int64_t R_bs = g->d_rows, Rr_bs = g->wr_elems;
+  L2I_CUDA_TRY(cudaMemsetAsync(g->R_s, 0, sizeof(float) * B * R_bs, st));
+  L2I_CUDA_TRY(cudaMemsetAsync(g->R_d, 0, sizeof(float) * B * R_bs, st));
+  L2I_CUDA_TRY(cudaMemsetAsync(g->R_rgb, 0, sizeof(float) * B * Rr_bs, st));
+
+  const float* g_skip = grad_image;  // gradient w.r.t. the skip image at the current resolution
+  const void* g_xn = nullptr;        // gradient w.r.t. the x~' output of the layer being processed
+  int gx_sel = 0;                    // act[0] / act[1] hold the data gradients (forward scratch is free now)
+  int gskip_sel = 0;
+  int rgb_i = (int)g->rgbs.size() - 1;
+  for (int li = (int)g->convs.size() - 1; li >= 0; --li) {
+    const auto& L = g->convs[li];
+    const StyledConvLayer* next = li + 1 < (int)g->convs.size() ? &g->convs[li + 1] : nullptr;
+    const float* s_next = next ? g->s_all + next->s_off : nullptr;
+    const float* demod = g->d_all + L.d_off;
+    const int HWo = L.res_out * L.res_out;
+    ConvGeom geom{};
+    geom.B = B; geom.Cin = L.cout; geom.Cout = L.cin; geom.nphase = 1; geom.out_scale = 1;
+    geom.OH = geom.OW = L.res_in; geom.out_H = geom.out_W = L.res_in;
+    EpiParams e{};
+    e.mode = 1; e.demod = nullptr;
+    void* gx_dst = g->act[gx_sel];
+    e.out = gx_dst;
+    if (!L.up) {
+      const auto& R = g->rgbs[rgb_i];
+      L2I_TRY(launch_act_bwd<T>(g->gbuf, g_xn, g_skip, L.y_save, s_next, g->s_rows, g->wr_all + R.wr_off, g->wr_elems, demod,
+                                g->d_rows, L.noise_ptr, L.noise_bs, P_noise_w(g, L), P_bias(g, L),
+                                next ? g->R_s + L.d_off : nullptr, g->R_d + L.d_off, R_bs, g->R_rgb + R.wr_off, Rr_bs, B, HWo,
+                                L.cout, st));
+      geom.H = geom.W = L.res_out; geom.in_scale = 1; geom.taps[0] = dgrad_plain_taps();
+      L2I_TRY(launch_conv_simt<T>(g->gbuf, L.w_f32_t, geom, e, st));
+      // skip chain: g_skip(res/2) = Upsample^T(g_skip(res)) = upfirdn2d(down=2, flipped kernel, pad (1,1))
+      if (rgb_i > 0) {
+        float* dst = g->gskip[gskip_sel];
+        L2I_TRY(l2i_upfirdn2d(dst, g_skip, g->fir2d_dev, (int64_t)B * 3, L.res_out, L.res_out, 1, 4, 4, 1, 1, 2, 2, 1, 1, 1, 1,
+                              L2I_F32, st));
+        g_skip = dst;
+        gskip_sel ^= 1;
+      }
+      --rgb_i;
+    } else {
+      // y -> g_v (no ToRGB, no demod here), then blur^T and the stride-2 gather conv
+      L2I_TRY(launch_act_bwd<T>(g->gbuf, g_xn, nullptr, L.y_save, s_next, g->s_rows, nullptr, 0, nullptr, 0, nullptr, 0, nullptr,
+                                nullptr, g->R_s + L.d_off, nullptr, R_bs, nullptr, 0, B, HWo, L.cout, st));
+      const int TH = 2 * L.res_in + 2;
+      L2I_TRY((launch_blur_bwd<T, TIN>(g->tbuf, g->gbuf, L.t_save, demod, g->d_rows, g->R_d + L.d_off, R_bs, B, L.res_out,
+                                       L.res_out, TH, TH, L.cout, g->fir, st)));
+      geom.H = geom.W = TH; geom.in_scale = 2; geom.taps[0] = dgrad_up_taps();
+      L2I_TRY(launch_conv_simt<T>(g->tbuf, L.w_f32_t, geom, e, st));
+    }
+    g_xn = gx_dst;
+    gx_sel ^= 1;
+  }
+  // conv1's input is the constant: its style gradient is sum_p g_x~ * const
+  const auto& L0 = g->convs[0];
+  const_grad_kernel<T><<<ceil_div(B * L0.cin, 256), 256, 0, st>>>(g->R_s0, L0.cin, (const T*)g_xn, P(g, "input.input"), B,
+                                                                 L0.cin, 16);
+  L2I_TRY(check_launch("const_grad"));
+
+  // style gradients per modulated conv, then through the modulation linears to the W+ latent
+  for (size_t li = 0; li < g->convs.size(); ++li) {
+    const auto& L = g->convs[li];
+    const float* Rs = li == 0 ? g->R_s0 : g->R_s + g->convs[li - 1].d_off;
+    const int64_t Rs_bs = li == 0 ? L.cin : R_bs;
+    conv_style_grad_kernel<<<ceil_div(B * L.cin * 32, 256), 256, 0, st>>>(g->gs_all + L.s_off, g->s_rows, Rs, Rs_bs,
+                                                                         g->s_all + L.s_off, g->s_rows, g->wsq_all + L.wsq_off,
+                                                                         g->d_all + L.d_off, g->R_d + L.d_off, g->d_rows, B,
+                                                                         L.cin, L.cout);
+    L2I_TRY(check_launch("conv_style_grad"));
+  }
+  for (auto& R : g->rgbs) {
+    rgb_style_grad_kernel<<<ceil_div(B * R.cin, 256), 256, 0, st>>>(g->gs_all + R.s_off, g->s_rows, g->wrgb_all + R.wr_off,
+                                                                   g->R_rgb + R.wr_off, Rr_bs, B, R.cin);
+    L2I_TRY(check_launch("rgb_style_grad"));
+  }
+  latent_grad_kernel<<<dim3(g->n_latent, B), 128, 0, st>>>(grad_latent, g->gs_all, g->s_rows, g->mod_w_all, g->lat_seg,
+                                                           g->n_latent, D);
+  return check_launch("latent_grad");
+}
+
+}  // namespace
+}  // namespace l2i
+
+using namespace l2i;
+
+extern "C" int l2i_generator_set_training(l2i_generator_t* g, int enable) {
+  L2I_REQUIRE(g, "generator_set_training: null generator");
+  if (!enable) { g->training = false; return L2I_OK; }
+  if (!g->finalized) { set_error("generator_set_training: call l2i_generator_finalize first"); return L2I_ERR_STATE; }
+  if (!g->train_buffers) {
+    const int64_t B = g->max_batch;
+    const int64_t es = (int64_t)g->elem_size();
+    int64_t act_elems = 0;
+    for (auto& L : g->convs) {
+      char* p = nullptr;
+      L2I_TRY(train_alloc(g, &p, B * L.res_out * L.res_out * (int64_t)L.cout * es));
+      L.y_save = p;
+      if (L.up) {
+        const int64_t th = 2 * L.res_in + 2;
+        L2I_TRY(train_alloc(g, &p, B * th * th * (int64_t)L.cout * es));
+        L.t_save = p;
+      }
+      L2I_TRY(train_alloc(g, &L.w_f32_t, (int64_t)9 * L.cin * L.cout));
+      act_elems = std::max(act_elems, B * L.res_out * L.res_out * (int64_t)L.cout);
+    }
+    char* gb = nullptr;
+    L2I_TRY(train_alloc(g, &gb, act_elems * es));
+    g->gbuf = gb;
+    L2I_TRY(train_alloc(g, &g->R_s, B * (int64_t)g->d_rows));
+    L2I_TRY(train_alloc(g, &g->R_d, B * (int64_t)g->d_rows));
+    L2I_TRY(train_alloc(g, &g->R_rgb, B * (int64_t)g->wr_elems));
+    L2I_TRY(train_alloc(g, &g->R_s0, B * (int64_t)g->convs[0].cin));
+    L2I_TRY(train_alloc(g, &g->gs_all, B * (int64_t)g->s_rows));
+    L2I_TRY(train_alloc(g, &g->gskip[0], B * 3 * (int64_t)(g->size / 2) * (g->size / 2)));
+    L2I_TRY(train_alloc(g, &g->gskip[1], B * 3 * (int64_t)(g->size / 4) * (g->size / 4)));
+    L2I_TRY(train_alloc(g, &g->fir2d_dev, 16));
+    L2I_TRY(train_alloc(g, &g->lat_seg, (int64_t)g->n_latent * 7));
+    // tables: which style rows read each latent index; the 2-D FIR of the skip up-sampling (flipped for the transpose)
+    std::vector<int> seg(g->n_latent * 7, 0);
+    auto add = [&](int lat, int r0, int n) {
+      int* s = &seg[lat * 7];
+      s[1 + 2 * s[0]] = r0; s[2 + 2 * s[0]] = n; ++s[0];
+    };
+    for (auto& L : g->convs) add(L.latent_idx, L.s_off, L.cin);
+    for (auto& R : g->rgbs) add(R.latent_idx, R.s_off, R.cin);
+    float k2[16];
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) k2[i * 4 + j] = g->fir[i] * g->fir[j];  // fir is already flipped: this is flip(kernel)
+    L2I_CUDA_TRY(cudaMemcpy(g->lat_seg, seg.data(), sizeof(int) * seg.size(), cudaMemcpyHostToDevice));
+    L2I_CUDA_TRY(cudaMemcpy(g->fir2d_dev, k2, sizeof(k2), cudaMemcpyHostToDevice));
+    g->train_buffers = true;
+  }
+  // data-gradient weight copies follow the current parameters
+  for (auto& L : g->convs) {
+    const float scale = 1.0f / std::sqrt((float)(L.cin * 9));
+    const int64_t total = (int64_t)L.cout * L.cin;
+    const int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)kNumSMs * 8);
+    pack_weight_t_kernel<<<blocks, 256>>>(L.w_f32_t, g->params.at(L.name + ".conv.weight").ptr, L.cout, L.cin, 9, scale);
+    L2I_TRY(check_launch("pack_weight_t"));
+  }
+  L2I_CUDA_TRY(cudaDeviceSynchronize());
+  g->training = true;
+  return L2I_OK;
+}
+
+extern "C" int l2i_generator_backward(l2i_generator_t* g, float* grad_latent, const float* grad_image, int batch, void* stream) {
+  L2I_REQUIRE(g && grad_latent && grad_image, "generator_backward: null argument");
+  if (!g->train_buffers || g->last_train_batch != batch) {
+    set_error("generator_backward: needs a forward in training mode with the same batch (last training batch %d, got %d)",
+              g->last_train_batch, batch);
+    return L2I_ERR_STATE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g->dtype == L2I_F32) return backward_impl<float>(g, grad_latent, grad_image, batch, st);
+  return backward_impl<__nv_bfloat16>(g, grad_latent, grad_image, batch, st);
+}

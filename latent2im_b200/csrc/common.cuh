@@ -37,9 +37,9 @@ inline int check_launch(const char* what) {
     }                                                                             \
   } while (0)
 
-#define L2I_TRY(expr)              \
+#define L2I_TRY(...)               \
   do {                             \
-    int rc__ = (expr);             \
+    int rc__ = (__VA_ARGS__);      \
     if (rc__ != L2I_OK) return rc__; \
   } while (0)
 

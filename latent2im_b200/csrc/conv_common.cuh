@@ -32,12 +32,14 @@ struct ConvGeom {
   int nphase;              // 1 (plain) or 4 (stride-2 transposed conv, phase-decomposed)
   TapList taps[4];
   int out_scale;           // 1 or 2: output pixel = (oy*out_scale + py, ox*out_scale + px)
+  int in_scale;            // 1, or 2 for the data gradient of the stride-2 transposed conv: input pixel = oy*in_scale + dy
   int out_H, out_W;        // allocated dims of the output tensor
 };
 
 struct EpiParams {
   int mode;                 // 0 = act, 1 = raw
-  const float* demod;       // [B][demod_bs]
+  int raw_fp16;             // raw mode with 16-bit storage: write fp16 (the demodulated conv output is bounded)
+  const float* demod;       // [B][demod_bs]; nullptr = 1 (data-gradient convs)
   int64_t demod_bs;
   const float* bias;        // [Cout]
   const float* noise;       // [Bn][H][W] fp32 or nullptr
@@ -46,6 +48,7 @@ struct EpiParams {
   const float* s_next;      // [B][s_next_bs] or nullptr (no activation output)
   int64_t s_next_bs;
   void* out;                // NHWC [B][out_H][out_W][Cout]
+  void* y_out;              // training: unscaled activation y (same layout), saved for the backward pass
   // ToRGB
   const float* wr;          // [B][wr_bs] laid out [3][Cout], or nullptr
   int64_t wr_bs;

@@ -45,7 +45,7 @@ conv_simt_kernel(const T* __restrict__ in, const float* __restrict__ wt, ConvGeo
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
   for (int t = 0; t < taps.n; ++t) {
-    const int iy = a_oy + taps.dy[t], ix = a_ox + taps.dx[t];
+    const int iy = a_oy * g.in_scale + taps.dy[t], ix = a_ox * g.in_scale + taps.dx[t];
     const bool inb = a_valid && iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
     const T* arow = in + (((int64_t)a_b * g.H + (inb ? iy : 0)) * g.W + (inb ? ix : 0)) * g.Cin;
     const float* wtap = wt + (int64_t)taps.wtap[t] * g.Cin * g.Cout;
@@ -96,7 +96,7 @@ conv_simt_kernel(const T* __restrict__ in, const float* __restrict__ wt, ConvGeo
     const int b = (int)(r / g.OH);
     const int Y = oy * g.out_scale + py, X = ox * g.out_scale + px;
     float rgb[3] = {0.f, 0.f, 0.f};
-    float outv[4];
+    float outv[4], yv[4];
     float nz = 0.f;
     if (e.mode == 0 && e.noise != nullptr && valid)
       nz = nw * e.noise[(int64_t)b * e.noise_bs + (int64_t)Y * g.out_W + X];
@@ -105,7 +105,7 @@ conv_simt_kernel(const T* __restrict__ in, const float* __restrict__ wt, ConvGeo
       const int co = co0 + j;
       float v = 0.f;
       if (co < g.Cout && valid) {
-        v = acc[i][j] * e.demod[(int64_t)b * e.demod_bs + co];
+        v = acc[i][j] * (e.demod != nullptr ? e.demod[(int64_t)b * e.demod_bs + co] : 1.f);
         if (e.mode == 0) {
           v = lrelu(v + nz + e.bias[co], 0.2f) * 1.4142135623730951f;
           if (e.wr != nullptr) {
@@ -113,16 +113,31 @@ conv_simt_kernel(const T* __restrict__ in, const float* __restrict__ wt, ConvGeo
 #pragma unroll
             for (int c = 0; c < 3; ++c) rgb[c] = fmaf(wr[c * g.Cout + co], v, rgb[c]);
           }
+          yv[j] = v;
           if (e.s_next != nullptr) v *= e.s_next[(int64_t)b * e.s_next_bs + co];
         }
       }
       outv[j] = v;
     }
     if (valid && e.out != nullptr && (e.mode == 1 || e.s_next != nullptr)) {
-      T* op = (T*)e.out + (((int64_t)b * g.out_H + Y) * g.out_W + X) * g.Cout + co0;
+      const int64_t off = (((int64_t)b * g.out_H + Y) * g.out_W + X) * g.Cout + co0;
+      if (sizeof(T) == 2 && e.mode == 1 && e.raw_fp16) {
+        __half* op = (__half*)e.out + off;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (co0 + j < g.Cout) op[j] = __float2half_rn(outv[j]);
+      } else {
+        T* op = (T*)e.out + off;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (co0 + j < g.Cout) op[j] = from_f32<T>(outv[j]);
+      }
+    }
+    if (valid && e.mode == 0 && e.y_out != nullptr) {
+      T* yp = (T*)e.y_out + (((int64_t)b * g.out_H + Y) * g.out_W + X) * g.Cout + co0;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (co0 + j < g.Cout) op[j] = from_f32<T>(outv[j]);
+        if (co0 + j < g.Cout) yp[j] = from_f32<T>(yv[j]);
     }
     if (e.mode == 0 && e.wr != nullptr) {
       // reduce the three partial sums over the 16 lanes that share this pixel

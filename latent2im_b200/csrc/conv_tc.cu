@@ -117,8 +117,8 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_
 
 // cute::UMMA::InstrDescriptor for kind::f16: c=F32 (1<<4), a=b=BF16 (1<<7, 1<<10), K-major A and B,
 // n_dim = N>>3 at bit 17, m_dim = M>>4 at bit 24.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int b_is_fp16 = 0) {
+  return (1u << 4) | (1u << 7) | ((b_is_fp16 ? 0u : 1u) << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 struct TcParams {
@@ -300,7 +300,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int co0 = nt * BLOCK_N;
         for (int j = gtid; j < BLOCK_N; j += 128) {
           const int co = co0 + j;
-          const float d = __ldg(e.demod + (int64_t)b * e.demod_bs + co);
+          const float d = e.demod != nullptr ? __ldg(e.demod + (int64_t)b * e.demod_bs + co) : 1.f;
           if (e.mode == 0) {
             s_d[j] = d * kSqrt2;
             s_b[j] = __ldg(e.bias + co) * kSqrt2;
@@ -332,6 +332,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       __nv_bfloat16* outp = nullptr;
       if (valid && e.out != nullptr && (e.mode == 1 || e.s_next != nullptr))
         outp = (__nv_bfloat16*)e.out + (((int64_t)b * p.out_H + Y) * p.out_W + X) * p.Cout + nt * BLOCK_N;
+      __nv_bfloat16* yp = nullptr;
+      if (valid && e.mode == 0 && e.y_out != nullptr)
+        yp = (__nv_bfloat16*)e.y_out + (((int64_t)b * p.out_H + Y) * p.out_W + X) * p.Cout + nt * BLOCK_N;
       float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
 
       mbar_wait(&tmem_full[group], acc_phase);
@@ -343,10 +346,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tmem_ld32(taddr + c0, v);
         tmem_ld_wait();
         uint32_t packed[16];
+        uint32_t ypacked[16];
 #pragma unroll
         for (int j4 = 0; j4 < 32; j4 += 4) {
           const float4 d4 = *reinterpret_cast<const float4*>(s_d + c0 + j4);
           float o[4];
+          float yy[4] = {0.f, 0.f, 0.f, 0.f};
           if (e.mode == 0) {
             const float4 b4 = *reinterpret_cast<const float4*>(s_b + c0 + j4);
             const float4 n4 = *reinterpret_cast<const float4*>(s_n + c0 + j4);
@@ -363,15 +368,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               rgb0 = fmaf(a0[h], x, rgb0);
               rgb1 = fmaf(a1[h], x, rgb1);
               rgb2 = fmaf(a2[h], x, rgb2);
+              yy[h] = x;
               o[h] = x * nn[h];
             }
           } else {
             o[0] = __uint_as_float(v[j4]) * d4.x; o[1] = __uint_as_float(v[j4 + 1]) * d4.y;
             o[2] = __uint_as_float(v[j4 + 2]) * d4.z; o[3] = __uint_as_float(v[j4 + 3]) * d4.w;
           }
-          __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
-          packed[j4 >> 1] = *reinterpret_cast<uint32_t*>(&p0);
-          packed[(j4 >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p1);
+          {
+            __nv_bfloat162 y0 = __floats2bfloat162_rn(yy[0], yy[1]), y1 = __floats2bfloat162_rn(yy[2], yy[3]);
+            ypacked[j4 >> 1] = *reinterpret_cast<uint32_t*>(&y0);
+            ypacked[(j4 >> 1) + 1] = *reinterpret_cast<uint32_t*>(&y1);
+          }
+          if (e.mode == 1 && e.raw_fp16) {
+            __half2 p0 = __floats2half2_rn(o[0], o[1]), p1 = __floats2half2_rn(o[2], o[3]);
+            packed[j4 >> 1] = *reinterpret_cast<uint32_t*>(&p0);
+            packed[(j4 >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p1);
+          } else {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
+            packed[j4 >> 1] = *reinterpret_cast<uint32_t*>(&p0);
+            packed[(j4 >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p1);
+          }
+        }
+        if (yp != nullptr) {
+          uint4* dst = reinterpret_cast<uint4*>(yp + c0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) dst[k] = make_uint4(ypacked[4 * k], ypacked[4 * k + 1], ypacked[4 * k + 2], ypacked[4 * k + 3]);
         }
         if (outp != nullptr) {
           uint4* dst = reinterpret_cast<uint4*>(outp + c0);
@@ -484,6 +506,7 @@ int pick_block_n(int cout) { return cout >= 256 ? 256 : cout; }
 
 bool conv_tc_supported(const ConvGeom& g, const EpiParams& e) {
   (void)e;
+  if (g.in_scale != 1) return false;  // strided-input data gradient runs on the CUDA-core kernel
   if (g.Cin % 32 != 0 || g.Cin < 32) return false;
   const int bn = pick_block_n(g.Cout);
   if (!(bn == 32 || bn == 64 || bn == 128 || bn == 256)) return false;
@@ -495,7 +518,7 @@ bool conv_tc_supported(const ConvGeom& g, const EpiParams& e) {
 
 int conv_tc_block_n(const ConvGeom& g) { return pick_block_n(g.Cout); }
 
-int launch_conv_tc(const void* in, const __nv_bfloat16* w, const ConvGeom& g, const EpiParams& e, cudaStream_t st) {
+int launch_conv_tc(const void* in, const __nv_bfloat16* w, int w_fp16, const ConvGeom& g, const EpiParams& e, cudaStream_t st) {
   TcParams p{};
   p.B = g.B; p.H = g.H; p.W = g.W; p.Cin = g.Cin; p.Cout = g.Cout;
   p.OH = g.OH; p.OW = g.OW; p.nphase = g.nphase; p.out_scale = g.out_scale; p.out_H = g.out_H; p.out_W = g.out_W;
@@ -511,7 +534,8 @@ int launch_conv_tc(const void* in, const __nv_bfloat16* w, const ConvGeom& g, co
   p.tiles_x = ceil_div(g.OW, bw); p.tiles_y = ceil_div(g.OH, bh);
   const int bn = pick_block_n(g.Cout);
   p.tiles_n = g.Cout / bn;
-  p.idesc = make_idesc_bf16(kBlockM, bn);
+  (void)w_fp16;  // mixed bf16 x fp16 operands raise an illegal-instruction fault on sm_100a: both stay bf16
+  p.idesc = make_idesc_bf16(kBlockM, bn, 0);
   const int64_t total = (int64_t)p.tiles_x * p.tiles_y * g.B * p.tiles_n * g.nphase;
   if (total <= 0 || total > 0x7fffffff) {
     set_error("conv_tc: bad tile count %lld", (long long)total);

@@ -8,121 +8,7 @@
 #include <unordered_map>
 #include <vector>
 
-#include "conv_common.cuh"
-
-namespace l2i {
-
-// kernels implemented in the other translation units
-template <typename T> int launch_conv_simt(const void*, const float*, const ConvGeom&, const EpiParams&, cudaStream_t);
-int launch_conv_tc(const void* in, const __nv_bfloat16* w, const ConvGeom& g, const EpiParams& e, cudaStream_t st);
-bool conv_tc_supported(const ConvGeom& g, const EpiParams& e);
-int conv_tc_block_n(const ConvGeom& g);
-template <typename T>
-int launch_blur_act(void*, const void*, int, int, int, int, int, int, const float*, int64_t, const float*,
-                    const float*, const float*, int64_t, const float*, cudaStream_t);
-int launch_skip_combine(float*, const float*, int, const float*, const float*, int, int, int, const float*, cudaStream_t);
-template <typename T> int launch_const_input(void*, const float*, const float*, int64_t, int, int, int, cudaStream_t);
-int launch_demod(float*, int64_t, const float*, int64_t, const float*, const int64_t*, const int*, const int*, int, int, cudaStream_t);
-int launch_rgb_weight(float*, int64_t, const float*, const int*, const float*, int64_t, int, int, cudaStream_t);
-int launch_gather_latent(float*, const float*, int64_t, int64_t, int, int, int, cudaStream_t);
-int launch_pack_conv_weight(float*, __nv_bfloat16*, float*, const float*, int, int, int, float, cudaStream_t);
-int launch_scale_copy(float*, const float*, int64_t, float, cudaStream_t);
-template <typename T> int launch_nhwc_to_nchw(float*, const void*, int, int, int, int, const float*, int64_t, cudaStream_t);
-int launch_linear(float*, int64_t, const float*, int64_t, const int*, const float*, const float*, int, int, int,
-                  float, float, int, float, float, cudaStream_t);
-
-struct Param {
-  float* ptr = nullptr;
-  int64_t numel = 0;
-  bool set = false;
-};
-
-struct StyledConvLayer {
-  std::string name;  // "conv1" or "convs.j"
-  int cin, cout, res_in, res_out;
-  bool up;
-  int latent_idx, noise_idx;
-  int s_off;   // offset of this layer's styles inside a row of s_all
-  int d_off;   // offset of this layer's demod coefficients inside a row of d_all
-  float* w_f32 = nullptr;            // [9][Cin][Cout]
-  __nv_bfloat16* w_bf16 = nullptr;   // [9][Cout][Cin]
-  int64_t wsq_off = 0;
-};
-
-struct RgbLayer {
-  std::string name;  // "to_rgb1" or "to_rgbs.k"
-  int cin, res, latent_idx;
-  int s_off;    // inside s_all row
-  int wr_off;   // inside wr_all row
-};
-
-}  // namespace l2i
-
-using namespace l2i;
-
-struct l2i_generator {
-  int size, D, n_mlp, cm, dtype, max_batch, log_size, num_layers, n_latent;
-  float lr_mlp;
-  float fir[4];  // flipped separable taps * 2 (== taps / sum * 2)
-  bool finalized = false;
-  int last_batch = 0;
-  int conv_impl = 0;  // 0 auto, 1 simt, 2 tc
-
-  std::unordered_map<std::string, Param> params;
-  std::vector<StyledConvLayer> convs;
-  std::vector<RgbLayer> rgbs;
-
-  // style tables
-  int s_rows = 0, d_rows = 0, wr_elems = 0;
-  float *mod_w_all = nullptr, *mod_b_all = nullptr;
-  int* row_xoff = nullptr;
-  float* wsq_all = nullptr;
-  int64_t* row_wsq_off = nullptr;
-  int *row_s_off = nullptr, *row_cin = nullptr;
-  float* wrgb_all = nullptr;
-  int* rgb_elem_s_off = nullptr;
-
-  // workspace
-  float *latent_buf = nullptr, *s_all = nullptr, *d_all = nullptr, *wr_all = nullptr;
-  void* act[2] = {nullptr, nullptr};
-  void* tbuf = nullptr;
-  float* rgb_part = nullptr;
-  float* skip[2] = {nullptr, nullptr};
-  float* map_buf[2] = {nullptr, nullptr};
-  // where each layer's output landed in the last forward (debug taps)
-  std::vector<const void*> conv_out;
-  std::vector<const float*> skip_out;
-
-  std::vector<void*> allocs;
-  size_t elem_size() const { return dtype == L2I_F32 ? 4 : 2; }
-
-  // optional per-segment timing (CUDA events on the caller's stream)
-  struct Segment {
-    std::string name;
-    int kind;          // 0 conv (tensor / FFMA bound), 1 blur_act, 2 skip / rgb, 3 styles & misc
-    double flops, bytes;
-    cudaEvent_t ev0, ev1;
-  };
-  bool profiling = false;
-  std::vector<Segment> segs;
-  size_t seg_used = 0;
-  Segment* seg_begin(const std::string& name, int kind, double flops, double bytes, cudaStream_t st) {
-    if (!profiling) return nullptr;
-    if (seg_used == segs.size()) {
-      Segment sg;
-      cudaEventCreate(&sg.ev0);
-      cudaEventCreate(&sg.ev1);
-      segs.push_back(sg);
-    }
-    Segment& sg = segs[seg_used++];
-    sg.name = name; sg.kind = kind; sg.flops = flops; sg.bytes = bytes;
-    cudaEventRecord(sg.ev0, st);
-    return &sg;
-  }
-  void seg_end(Segment* sg, cudaStream_t st) {
-    if (sg) cudaEventRecord(sg->ev1, st);
-  }
-};
+#include "generator_internal.cuh"
 
 namespace {
 
@@ -139,19 +25,7 @@ int channels_at(int res, int cm) {
 }
 
 template <typename T>
-int dev_alloc(l2i_generator* g, T** p, int64_t n) {
-  *p = nullptr;
-  if (n <= 0) return L2I_OK;
-  void* q = nullptr;
-  cudaError_t e = cudaMalloc(&q, (size_t)n * sizeof(T));
-  if (e != cudaSuccess) {
-    set_error("generator: cudaMalloc(%lld bytes) failed: %s", (long long)(n * (int64_t)sizeof(T)), cudaGetErrorString(e));
-    return L2I_ERR_CUDA;
-  }
-  g->allocs.push_back(q);
-  *p = (T*)q;
-  return L2I_OK;
-}
+int dev_alloc(l2i_generator* g, T** p, int64_t n) { return train_alloc(g, p, n); }
 
 int add_param(l2i_generator* g, const std::string& key, int64_t numel) {
   Param p;
@@ -160,8 +34,6 @@ int add_param(l2i_generator* g, const std::string& key, int64_t numel) {
   g->params[key] = p;
   return L2I_OK;
 }
-
-float* P(l2i_generator* g, const std::string& key) { return g->params.at(key).ptr; }
 
 TapList plain_taps() {
   TapList t{};
@@ -195,7 +67,7 @@ int run_conv(l2i_generator* g, const StyledConvLayer& L, const void* in, const C
              cudaStream_t st) {
   if (g->dtype == L2I_F32) return launch_conv_simt<float>(in, L.w_f32, geom, e, st);
   const bool want_tc = g->conv_impl != 1;
-  if (want_tc && conv_tc_supported(geom, e)) return launch_conv_tc(in, L.w_bf16, geom, e, st);
+  if (want_tc && conv_tc_supported(geom, e)) return launch_conv_tc(in, L.w_bf16, g->weight_fp16, geom, e, st);
   if (g->conv_impl == 2) {
     set_error("generator: L2I_CONV_IMPL=tc but layer %s is not supported by the tcgen05 kernel", L.name.c_str());
     return L2I_ERR_UNSUPPORTED;
@@ -410,7 +282,7 @@ extern "C" int l2i_generator_finalize(l2i_generator_t* g, void* stream) {
   for (auto& L : g->convs) {
     const float scale = 1.0f / std::sqrt((float)(L.cin * 9));
     L2I_TRY(launch_pack_conv_weight(L.w_f32, L.w_bf16, g->wsq_all + L.wsq_off, P(g, L.name + ".conv.weight"), L.cout,
-                                    L.cin, 9, scale, st));
+                                    L.cin, 9, scale, g->weight_fp16, st));
     L2I_TRY(launch_scale_copy(g->mod_w_all + (int64_t)L.s_off * D, P(g, L.name + ".conv.modulation.weight"),
                               (int64_t)L.cin * D, mod_scale, st));
     L2I_TRY(launch_scale_copy(g->mod_b_all + L.s_off, P(g, L.name + ".conv.modulation.bias"), L.cin, 1.f, st));
@@ -497,7 +369,9 @@ extern "C" int l2i_generator_forward(l2i_generator_t* g, const float* latent, in
     const float* s_next = next ? g->s_all + next->s_off : nullptr;
 
     ConvGeom geom{};
-    geom.B = B; geom.H = geom.W = L.res_in; geom.Cin = L.cin; geom.Cout = L.cout;
+    geom.B = B; geom.H = geom.W = L.res_in; geom.Cin = L.cin; geom.Cout = L.cout; geom.in_scale = 1;
+    const bool keep = g->training;
+    if (keep) { g->convs[li].noise_ptr = nz; g->convs[li].noise_bs = nz_bs; }
     EpiParams e{};
     e.demod = g->d_all + L.d_off; e.demod_bs = g->d_rows;
     for (int i = 0; i < 4; ++i) e.fir[i] = g->fir[i];
@@ -506,7 +380,8 @@ extern "C" int l2i_generator_forward(l2i_generator_t* g, const float* latent, in
       geom.OH = geom.OW = L.res_in + 1; geom.nphase = 4; geom.out_scale = 2;
       geom.out_H = geom.out_W = 2 * L.res_in + 2;
       for (int ph = 0; ph < 4; ++ph) geom.taps[ph] = upconv_taps(ph >> 1, ph & 1);
-      e.mode = 1; e.out = g->tbuf;
+      void* tdst = keep ? L.t_save : g->tbuf;
+      e.mode = 1; e.out = tdst; e.raw_fp16 = f32 ? 0 : 1;
       const double px_in = (double)B * L.res_in * L.res_in, px_out = (double)B * L.res_out * L.res_out;
       const double px_t = (double)B * (2.0 * L.res_in + 1) * (2.0 * L.res_in + 1);
       auto* sg_c = g->seg_begin(L.name + "/upconv", 0, 2.0 * 9 * L.cin * L.cout * px_in,
@@ -515,9 +390,9 @@ extern "C" int l2i_generator_forward(l2i_generator_t* g, const float* latent, in
       g->seg_end(sg_c, st);
       auto* sg_b = g->seg_begin(L.name + "/blur_act", 1, 0.0, (px_t + px_out) * L.cout * es + px_out * 4.0, st);
       void* dst = g->act[cur ^ 1];
-      if (f32) L2I_TRY(launch_blur_act<float>(dst, g->tbuf, B, L.res_out, L.res_out, L.cout, geom.out_H, geom.out_W, nz, nz_bs, nz_w,
+      if (f32) L2I_TRY(launch_blur_act<float, float>(dst, keep ? L.y_save : nullptr, tdst, B, L.res_out, L.res_out, L.cout, geom.out_H, geom.out_W, nz, nz_bs, nz_w,
                                               P(g, L.name + ".activate.bias"), s_next, g->s_rows, g->fir, st));
-      else L2I_TRY(launch_blur_act<__nv_bfloat16>(dst, g->tbuf, B, L.res_out, L.res_out, L.cout, geom.out_H, geom.out_W, nz, nz_bs,
+      else L2I_TRY(launch_blur_act<__nv_bfloat16, __half>(dst, keep ? L.y_save : nullptr, tdst, B, L.res_out, L.res_out, L.cout, geom.out_H, geom.out_W, nz, nz_bs,
                                                   nz_w, P(g, L.name + ".activate.bias"), s_next, g->s_rows, g->fir, st));
       g->seg_end(sg_b, st);
       cur ^= 1;
@@ -534,6 +409,7 @@ extern "C" int l2i_generator_forward(l2i_generator_t* g, const float* latent, in
     e.noise = nz; e.noise_bs = nz_bs; e.noise_w = nz_w;
     e.s_next = s_next; e.s_next_bs = g->s_rows;
     e.out = s_next ? g->act[cur ^ 1] : nullptr;
+    e.y_out = keep ? L.y_save : nullptr;
     e.wr = g->wr_all + R.wr_off; e.wr_bs = g->wr_elems;
     e.rgb_bias = P(g, R.name + ".bias");
     e.skip_in = skip_prev;
@@ -567,6 +443,7 @@ extern "C" int l2i_generator_forward(l2i_generator_t* g, const float* latent, in
     g->seg_end(sg_u, st);
   }
   g->last_batch = B;
+  if (g->training) g->last_train_batch = B;
   return L2I_OK;
 }
 
@@ -592,12 +469,6 @@ extern "C" int l2i_generator_profile_entry(l2i_generator_t* g, int i, char* name
   if (flops) *flops = sg.flops;
   if (bytes) *bytes = sg.bytes;
   return L2I_OK;
-}
-
-extern "C" int l2i_generator_backward(l2i_generator_t* g, float* grad_latent, const float* grad_image, int batch, void* stream) {
-  (void)g; (void)grad_latent; (void)grad_image; (void)batch; (void)stream;
-  set_error("generator_backward: not implemented in this build");
-  return L2I_ERR_UNSUPPORTED;
 }
 
 extern "C" int l2i_generator_read_activation(l2i_generator_t* g, const char* name, float* out, int64_t numel, int batch,

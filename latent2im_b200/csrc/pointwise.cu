@@ -26,13 +26,14 @@ struct alignas(sizeof(T) * VEC) TVec { T v[VEC]; };
 // element is written once with a 16-byte store.  Per-thread bias / next-style values live in registers.
 constexpr int kBlurRows = 32;
 
-template <typename T, int VEC>
+template <typename T, typename TIN, int VEC>
 __global__ void __launch_bounds__(256)
-blur_act_kernel(T* __restrict__ out, const T* __restrict__ t, int B, int OH, int OW, int C, int TH, int TW,
+blur_act_kernel(T* __restrict__ out, T* __restrict__ y_out, const TIN* __restrict__ t, int B, int OH, int OW, int C, int TH, int TW,
                 const float* __restrict__ noise, int64_t noise_bs, const float* __restrict__ noise_w,
                 const float* __restrict__ bias, const float* __restrict__ s_next, int64_t s_next_bs,
                 float f0, float f1, float f2, float f3, int VP, int tiles_x, int tiles_y, int chunks) {
   using V = TVec<T, VEC>;
+  using VIN = TVec<TIN, VEC>;
   constexpr float kSqrt2 = 1.4142135623730951f;
   const int XT = 256 / VP;
   int r = blockIdx.x;
@@ -52,21 +53,21 @@ blur_act_kernel(T* __restrict__ out, const T* __restrict__ t, int B, int OH, int
     bs[k] = __ldg(bias + c + k) * kSqrt2;
     sn[k] = s_next != nullptr ? __ldg(s_next + (int64_t)b * s_next_bs + c + k) : 1.f;
   }
-  const T* tb = t + (int64_t)b * TH * TW * C + c;
+  const TIN* tb = t + (int64_t)b * TH * TW * C + c;
   const float f[4] = {f0, f1, f2, f3};
 
   auto hrow = [&](int u, float (&h)[VEC]) {
 #pragma unroll
     for (int k = 0; k < VEC; ++k) h[k] = 0.f;
     if (u < 0 || u >= TH) return;
-    const T* row = tb + (int64_t)u * TW * C;
+    const TIN* row = tb + (int64_t)u * TW * C;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int v = X + j - 1;
       if (v < 0 || v >= TW) continue;
-      const V tv = *reinterpret_cast<const V*>(row + (int64_t)v * C);
+      const VIN tv = *reinterpret_cast<const VIN*>(row + (int64_t)v * C);
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) h[k] = fmaf(f[j], to_f32<T>(tv.v[k]), h[k]);
+      for (int k = 0; k < VEC; ++k) h[k] = fmaf(f[j], to_f32<TIN>(tv.v[k]), h[k]);
     }
   };
 
@@ -80,7 +81,7 @@ blur_act_kernel(T* __restrict__ out, const T* __restrict__ t, int B, int OH, int
   for (int Y = Y0; Y < Y1; ++Y) {
     hrow(Y + 2, h3);
     const float nz = nrow != nullptr ? nw * __ldg(nrow + (int64_t)Y * OW) : 0.f;
-    V ov;
+    V ov, yv;
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
       float a = f0 * h0[k];
@@ -89,15 +90,17 @@ blur_act_kernel(T* __restrict__ out, const T* __restrict__ t, int B, int OH, int
       a = fmaf(f3, h3[k], a);
       float x = fmaf(a, kSqrt2, bs[k] + nz);
       x = fmaxf(x, 0.2f * x);
+      yv.v[k] = from_f32<T>(x);
       ov.v[k] = from_f32<T>(x * sn[k]);
       h0[k] = h1[k]; h1[k] = h2[k]; h2[k] = h3[k];
     }
     *reinterpret_cast<V*>(ob + (int64_t)Y * OW * C) = ov;
+    if (y_out != nullptr) *reinterpret_cast<V*>(y_out + ((int64_t)b * OH * OW + X) * C + c + (int64_t)Y * OW * C) = yv;
   }
 }
 
-template <typename T>
-int launch_blur_act(void* out, const void* t, int B, int OH, int OW, int C, int TH, int TW, const float* noise,
+template <typename T, typename TIN>
+int launch_blur_act(void* out, void* y_out, const void* t, int B, int OH, int OW, int C, int TH, int TW, const float* noise,
                     int64_t noise_bs, const float* noise_w, const float* bias, const float* s_next,
                     int64_t s_next_bs, const float* f, cudaStream_t st) {
   constexpr int VEC = 16 / sizeof(T);
@@ -127,16 +130,16 @@ int launch_blur_act(void* out, const void* t, int B, int OH, int OW, int C, int 
     set_error("blur_act: grid too large");
     return L2I_ERR_INVALID_ARG;
   }
-  blur_act_kernel<T, VEC><<<(unsigned)blocks, 256, 0, st>>>((T*)out, (const T*)t, B, OH, OW, C, TH, TW, noise, noise_bs,
+  blur_act_kernel<T, TIN, VEC><<<(unsigned)blocks, 256, 0, st>>>((T*)out, (T*)y_out, (const TIN*)t, B, OH, OW, C, TH, TW, noise, noise_bs,
                                                            noise_w, bias, s_next, s_next_bs, f[0], f[1], f[2], f[3], VP,
                                                            tiles_x, tiles_y, chunks);
   return check_launch("blur_act");
 }
-template int launch_blur_act<float>(void*, const void*, int, int, int, int, int, int, const float*, int64_t,
-                                    const float*, const float*, const float*, int64_t, const float*, cudaStream_t);
-template int launch_blur_act<__nv_bfloat16>(void*, const void*, int, int, int, int, int, int, const float*, int64_t,
-                                            const float*, const float*, const float*, int64_t, const float*,
-                                            cudaStream_t);
+template int launch_blur_act<float, float>(void*, void*, const void*, int, int, int, int, int, int, const float*, int64_t,
+                                           const float*, const float*, const float*, int64_t, const float*, cudaStream_t);
+template int launch_blur_act<__nv_bfloat16, __half>(void*, void*, const void*, int, int, int, int, int, int, const float*,
+                                                    int64_t, const float*, const float*, const float*, int64_t,
+                                                    const float*, cudaStream_t);
 
 // ------------------------------------------------------------------------------------------------
 // skip_out[b,c,Y,X] = sum_p rgb_part[p][b][c][Y][X] + bias[c] + upsample2x(skip_in)[b,c,Y,X]
@@ -282,7 +285,7 @@ int launch_gather_latent(float* out, const float* in, int64_t bs, int64_t ls, in
 // wsq: [Cout][Cin] = sum_tap (scale*w)^2
 __global__ void pack_conv_weight_kernel(float* __restrict__ dst_f32, __nv_bfloat16* __restrict__ dst_bf16,
                                         float* __restrict__ wsq, const float* __restrict__ src, int Cout, int Cin,
-                                        int ntap, float scale) {
+                                        int ntap, float scale, int as_fp16) {
   const int64_t total = (int64_t)Cout * Cin;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
@@ -293,17 +296,21 @@ __global__ void pack_conv_weight_kernel(float* __restrict__ dst_f32, __nv_bfloat
       const float w = src[idx * ntap + t] * scale;
       ss = fmaf(w, w, ss);
       if (dst_f32) dst_f32[((int64_t)t * Cin + ci) * Cout + co] = w;
-      if (dst_bf16) dst_bf16[((int64_t)t * Cout + co) * Cin + ci] = __float2bfloat16_rn(w);
+      if (dst_bf16) {
+        const int64_t o = ((int64_t)t * Cout + co) * Cin + ci;
+        if (as_fp16) reinterpret_cast<__half*>(dst_bf16)[o] = __float2half_rn(w);  // same 16-bit slot, fp16 encoding
+        else dst_bf16[o] = __float2bfloat16_rn(w);
+      }
     }
     if (wsq) wsq[idx] = ss;
   }
 }
 
 int launch_pack_conv_weight(float* dst_f32, __nv_bfloat16* dst_bf16, float* wsq, const float* src, int Cout,
-                            int Cin, int ntap, float scale, cudaStream_t st) {
+                            int Cin, int ntap, float scale, int as_fp16, cudaStream_t st) {
   const int64_t total = (int64_t)Cout * Cin;
   const int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)kNumSMs * 8);
-  pack_conv_weight_kernel<<<blocks, 256, 0, st>>>(dst_f32, dst_bf16, wsq, src, Cout, Cin, ntap, scale);
+  pack_conv_weight_kernel<<<blocks, 256, 0, st>>>(dst_f32, dst_bf16, wsq, src, Cout, Cin, ntap, scale, as_fp16);
   return check_launch("pack_conv_weight");
 }
 

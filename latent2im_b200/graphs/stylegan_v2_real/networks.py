@@ -153,6 +153,7 @@ class _NativeHandle:
                                               gen.channel_multiplier, taps, len(gen.blur_kernel), float(gen.lr_mlp),
                                               nt.dtype_code(dtype), max_batch), "generator_create")
         self.version = None
+        self.training = False
 
     def upload(self, gen):
         version = tuple((p.data_ptr(), p._version) for p in gen.parameters())
@@ -176,6 +177,33 @@ class _NativeHandle:
                 self.lib.l2i_generator_destroy(self.handle)
         except Exception:
             pass
+
+
+class _SynthesisFn(torch.autograd.Function):
+    """Differentiable synthesis: forward in training mode (activations kept natively), backward =
+    ``l2i_generator_backward`` (data gradient w.r.t. the W+ latent only; the generator is frozen)."""
+
+    @staticmethod
+    def forward(ctx, latent, gen, noise):
+        image = gen._synthesize(latent, noise=noise, training=True)
+        ctx.gen = gen
+        ctx.token = gen._last_train
+        ctx.lat_shape = latent.shape
+        return image
+
+    @staticmethod
+    def backward(ctx, grad_image):
+        gen = ctx.gen
+        if gen._last_train is not ctx.token:
+            raise RuntimeError("Generator backward: another training-mode forward ran before this backward; "
+                               "the native library keeps the activations of one forward at a time")
+        h, batch, _ = ctx.token
+        g = grad_image.contiguous().float()
+        grad_latent = torch.empty(ctx.lat_shape, device=g.device, dtype=torch.float32)
+        with torch.cuda.device(g.device):
+            nt.check(h.lib.l2i_generator_backward(h.handle, grad_latent.data_ptr(), g.data_ptr(), batch, nt.stream_ptr(g.device)),
+                     "generator_backward")
+        return grad_latent, None, None
 
 
 class Generator(nn.Module):
@@ -269,6 +297,7 @@ class Generator(nn.Module):
         state = self.__dict__.copy()
         state["_native"] = {}
         state.pop("_last", None)
+        state.pop("_last_train", None)
         return state
 
     def __setstate__(self, state):
@@ -322,6 +351,14 @@ class Generator(nn.Module):
         return out
 
     def synthesize(self, latent, noise=None, randomize_noise=True, want_uint8=False, want_float=True):
+        if torch.is_grad_enabled() and latent.requires_grad:
+            if want_uint8:
+                raise RuntimeError("the uint8 image is not differentiable; call synthesize under torch.no_grad()")
+            nz = self._noise_list(latent.shape[0], latent.device, noise, randomize_noise)
+            return _SynthesisFn.apply(latent, self, nz)
+        return self._synthesize(latent, noise, randomize_noise, want_uint8, want_float, training=False)
+
+    def _synthesize(self, latent, noise=None, randomize_noise=True, want_uint8=False, want_float=True, training=False):
         """``latent`` [B, n_latent, D] -> image [B, 3, size, size] float32 (and / or the uint8 NHWC
         image ``clip((x + 1) / 2 * 255)`` the reference computes on the host, transform_base.py:625-626)."""
         device = latent.device
@@ -338,9 +375,14 @@ class Generator(nn.Module):
         image = torch.empty(batch, 3, self.size, self.size, device=device, dtype=torch.float32) if want_float else None
         image_u8 = torch.empty(batch, self.size, self.size, 3, device=device, dtype=torch.uint8) if want_uint8 else None
         with torch.cuda.device(device):
+            if training or h.training:
+                nt.check(h.lib.l2i_generator_set_training(h.handle, 1 if training else 0), "generator_set_training")
+                h.training = training
             nt.check(h.lib.l2i_generator_forward(h.handle, lat.data_ptr(), lat.stride(0), lat.stride(1), nz_ptrs, nz_batch,
                                                  nt.ptr(image), nt.ptr(image_u8), batch, nt.stream_ptr(device)),
                      "generator_forward")
+        if training:
+            self._last_train = (h, batch, nz)  # the noise tensors must outlive the backward pass
         self._last = (h, batch, nz)  # keeps the noise tensors alive until the next call
         if want_uint8 and want_float:
             return image, image_u8

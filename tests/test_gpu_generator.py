@@ -169,3 +169,55 @@ def test_tcgen05_conv_matches_cuda_core_conv(size, batch, monkeypatch):
         gen.set_native(dtype=torch.bfloat16)
         imgs[impl], _ = gen(lat, input_is_latent=True, noise=noise)
     assert _psnr(imgs["tc"].double(), imgs["simt"].double()) >= 46.0
+
+
+@pytest.mark.parametrize("size,dim,n_mlp,batch", [(8, 32, 1, 2), (16, 64, 2, 2), (32, 64, 1, 1)])
+def test_fp32_latent_gradient_matches_oracle_autograd(size, dim, n_mlp, batch):
+    """Data gradient w.r.t. the W+ latent (walk-training path) vs autograd through the float64 oracle."""
+    gen, sd, spec = _build(size, dim, n_mlp)
+    gen.set_native(dtype=torch.float32)
+    lat = _latent(spec, batch)
+    noise = synthetic_noise(spec.num_layers, batch)
+    probe = torch.randn(batch, 3, size, size, generator=torch.Generator().manual_seed(9))
+    lr = lat.double().requires_grad_(True)
+    ref = generator_forward_ref(sd, lr, noise, spec)
+    (gref,) = torch.autograd.grad((ref * probe.double()).sum(), lr)
+    lc = lat.cuda().requires_grad_(True)
+    img, _ = gen(lc, input_is_latent=True, noise=[n.cuda() for n in noise])
+    (img * probe.cuda()).sum().backward()
+    g = lc.grad.cpu().double()
+    scale = gref.abs().max().item()
+    assert (g - gref).abs().max().item() <= 2e-3 * scale, ((g - gref).abs().max().item(), scale)
+
+
+def test_latent_gradient_against_reference_goldens():
+    """fp32 kernels vs the gradient the UNMODIFIED reference's autograd produced on a B200."""
+    import os
+    import numpy as np
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_gpu_generator.npz"))
+    for size in (16, 32):
+        size_, dim, n_mlp, batch = [int(v) for v in z[f"s{size}_cfg"]]
+        gen, sd, spec = _build(size, dim, n_mlp, seed=size)
+        gen.set_native(dtype=torch.float32)
+        lat = torch.from_numpy(z[f"s{size}_latent"]).cuda().requires_grad_(True)
+        noise = [n.cuda() for n in synthetic_noise(spec.num_layers, batch, seed=2)]
+        img, _ = gen(lat, input_is_latent=True, noise=noise)
+        (img * torch.from_numpy(z[f"s{size}_probe"]).cuda()).sum().backward()
+        gref = torch.from_numpy(z[f"s{size}_grad_latent"])
+        assert (lat.grad.cpu() - gref).abs().max().item() <= 2e-3 * gref.abs().max().item()
+
+
+def test_bf16_latent_gradient_direction():
+    gen, sd, spec = _build(32, 64, 1)
+    lat = _latent(spec, 2)
+    noise = synthetic_noise(spec.num_layers, 2)
+    probe = torch.randn(2, 3, 32, 32, generator=torch.Generator().manual_seed(9))
+    grads = {}
+    for dt in (torch.float32, torch.bfloat16):
+        gen.set_native(dtype=dt)
+        lc = lat.cuda().requires_grad_(True)
+        img, _ = gen(lc, input_is_latent=True, noise=[n.cuda() for n in noise])
+        (img * probe.cuda()).sum().backward()
+        grads[dt] = lc.grad.flatten().double()
+    cos = torch.nn.functional.cosine_similarity(grads[torch.float32], grads[torch.bfloat16], dim=0).item()
+    assert cos >= 0.995, cos
