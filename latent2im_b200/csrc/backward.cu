@@ -323,7 +323,7 @@ int backward_impl(l2i_generator* g, float* grad_latent, const float* grad_image,
     const float* demod = g->d_all + L.d_off;
     const int HWo = L.res_out * L.res_out;
     ConvGeom geom{};
-    geom.B = B; geom.Cin = L.cout; geom.Cout = L.cin; geom.nphase = 1; geom.out_scale = 1;
+    geom.B = B; geom.Cin = L.cout; geom.Cout = L.cin; geom.nphase = 1; geom.out_scale = 1; geom.weight_taps = 9;
     geom.OH = geom.OW = L.res_in; geom.out_H = geom.out_W = L.res_in;
     EpiParams e{};
     e.mode = 1; e.demod = nullptr;

@@ -17,7 +17,7 @@
 
 namespace l2i {
 
-constexpr int kMaxTaps = 9;
+constexpr int kMaxTaps = 18;  // 9 spatial taps x (hi, lo) halves of split-bf16 weights
 
 struct TapList {
   int n;
@@ -34,6 +34,8 @@ struct ConvGeom {
   int out_scale;           // 1 or 2: output pixel = (oy*out_scale + py, ox*out_scale + px)
   int in_scale;            // 1, or 2 for the data gradient of the stride-2 transposed conv: input pixel = oy*in_scale + dy
   int out_H, out_W;        // allocated dims of the output tensor
+  int in_pair_packed;      // Cin == 32 input stored as [B][H/2][W][2][32]: vertical pixel pairs form 128-byte units
+  int weight_taps;         // tap slices in the packed weight tensor: 9, or 18 when it holds bf16 hi + lo halves
 };
 
 struct EpiParams {
@@ -62,28 +64,38 @@ struct EpiParams {
 
 // 2x FIR upsample of the low-res skip at output pixel (Y, X): reference Upsample (networks.py:30-48)
 // = upfirdn2d(up=2, pad=(2,1)) with kernel outer(taps)/sum*4.  f[] holds the *flipped* 1-D taps times 2.
+//   out[Y] = sum_i f[i] * U[Y + i - 2],  U[2y] = in[y], zero elsewhere / outside.
+// Exactly two input rows (and two columns) contribute to any output pixel:
+//   Y = 2m   : rows m-1 (f[0]) and m   (f[2]);      Y = 2m+1 : rows m (f[1]) and m+1 (f[3])
+// so the gather is 4 branch-free loads per channel (out-of-range taps get weight 0 and a clamped address).
+struct Up2Taps {
+  int y0, y1, x0, x1;
+  float wy0, wy1, wx0, wx1;
+};
+
+__device__ __forceinline__ Up2Taps make_up2_taps(int h, int w, int Y, int X, const float* f) {
+  Up2Taps t;
+  const int py = Y & 1, px = X & 1;
+  const int ya = (Y >> 1) - 1 + py, xa = (X >> 1) - 1 + px;
+  t.wy0 = (ya >= 0 && ya < h) ? f[py] : 0.f;
+  t.wy1 = (ya + 1 >= 0 && ya + 1 < h) ? f[py + 2] : 0.f;
+  t.wx0 = (xa >= 0 && xa < w) ? f[px] : 0.f;
+  t.wx1 = (xa + 1 >= 0 && xa + 1 < w) ? f[px + 2] : 0.f;
+  t.y0 = min(max(ya, 0), h - 1); t.y1 = min(max(ya + 1, 0), h - 1);
+  t.x0 = min(max(xa, 0), w - 1); t.x1 = min(max(xa + 1, 0), w - 1);
+  return t;
+}
+
+__device__ __forceinline__ float up2_apply(const float* __restrict__ plane, int w, const Up2Taps& t) {
+  const float a = __ldg(plane + (int64_t)t.y0 * w + t.x0), b = __ldg(plane + (int64_t)t.y0 * w + t.x1);
+  const float c = __ldg(plane + (int64_t)t.y1 * w + t.x0), d = __ldg(plane + (int64_t)t.y1 * w + t.x1);
+  return t.wy0 * (t.wx0 * a + t.wx1 * b) + t.wy1 * (t.wx0 * c + t.wx1 * d);
+}
+
 __device__ __forceinline__ float upsample2x_at(const float* __restrict__ plane, int h, int w, int Y, int X,
                                                const float* f) {
-  // out[Y] = sum_i f[i] * U[Y + i - 2], U[2y] = in[y], zero elsewhere / outside
-  float acc = 0.f;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int u = Y + i - 2;
-    if (u < 0 || (u & 1)) continue;
-    const int y = u >> 1;
-    if (y >= h) continue;
-    float row = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int v = X + j - 2;
-      if (v < 0 || (v & 1)) continue;
-      const int x = v >> 1;
-      if (x >= w) continue;
-      row = fmaf(f[j], plane[(int64_t)y * w + x], row);
-    }
-    acc = fmaf(f[i], row, acc);
-  }
-  return acc;
+  const Up2Taps t = make_up2_taps(h, w, Y, X, f);
+  return up2_apply(plane, w, t);
 }
 
 }  // namespace l2i

@@ -13,113 +13,13 @@
 //                                           next-style scale/ToRGB/skip -> global stores
 // Pipelines: smem ring (full/empty mbarriers, TMA <-> MMA) and a 2-deep TMEM accumulator ring
 // (tmem_full/tmem_empty, MMA <-> epilogue) so the epilogue of tile i overlaps the MMAs of tile i+1.
-#include <cuda.h>
-
-#include "conv_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace l2i {
 
+using namespace tc;
+
 namespace {
-
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols));
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate, issued by one thread
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp): rows are
-// swizzle_bytes wide, 8-row groups are `sbo` bytes apart, version = 1 (Blackwell).
-__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);              // start address  [0,14)
-  d |= (uint64_t)0 << 16;                                  // leading byte offset (unused: one atom along K)
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;        // stride byte offset [32,46)
-  d |= (uint64_t)1 << 46;                                  // version [46,48)
-  d |= (uint64_t)(layout_type & 7) << 61;                  // layout type [61,64): 2 = SW128, 4 = SW64
-  return d;
-}
-
-// cute::UMMA::InstrDescriptor for kind::f16: c=F32 (1<<4), a=b=BF16 (1<<7, 1<<10), K-major A and B,
-// n_dim = N>>3 at bit 17, m_dim = M>>4 at bit 24.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int b_is_fp16 = 0) {
-  return (1u << 4) | (1u << 7) | ((b_is_fp16 ? 0u : 1u) << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 
 struct TcParams {
   int B, H, W, Cin, Cout;
@@ -130,6 +30,7 @@ struct TcParams {
   int total_tiles;
   uint32_t a_bytes;               // bytes one A box load delivers (bw*bh*BLOCK_K*2)
   uint32_t idesc;                 // UMMA instruction descriptor (operand formats chosen on the host)
+  int weight_taps;                // 9 or 18 tap slices in the weight tensor
   EpiParams e;
 };
 
@@ -450,6 +351,9 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+}  // namespace
+
+namespace tc {
 int make_tmap(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
               const uint32_t* box, CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = get_encode_fn();
@@ -470,6 +374,11 @@ int make_tmap(CUtensorMap* map, const void* base, int rank, const uint64_t* dims
   return L2I_OK;
 }
 
+bool tmap_available() { return get_encode_fn() != nullptr; }
+}  // namespace tc
+
+namespace {
+
 template <int BLOCK_N, int BLOCK_K, int STAGES, int GROUPS>
 int launch_variant(const void* in, const __nv_bfloat16* w, TcParams& p, cudaStream_t st) {
   using L = SmemLayout<BLOCK_N, BLOCK_K, STAGES, GROUPS>;
@@ -484,7 +393,7 @@ int launch_variant(const void* in, const __nv_bfloat16* w, TcParams& p, cudaStre
     L2I_TRY(make_tmap(&ta, in, 4, dims, str, box, swz));
   }
   {
-    const uint64_t dims[3] = {(uint64_t)p.Cin, (uint64_t)p.Cout, 9};
+    const uint64_t dims[3] = {(uint64_t)p.Cin, (uint64_t)p.Cout, (uint64_t)p.weight_taps};
     const uint64_t str[3] = {2, (uint64_t)p.Cin * 2, (uint64_t)p.Cout * p.Cin * 2};
     const uint32_t box[3] = {(uint32_t)BLOCK_K, (uint32_t)BLOCK_N, 1};
     L2I_TRY(make_tmap(&tb, w, 3, dims, str, box, swz));
@@ -518,7 +427,7 @@ bool conv_tc_supported(const ConvGeom& g, const EpiParams& e) {
 
 int conv_tc_block_n(const ConvGeom& g) { return pick_block_n(g.Cout); }
 
-int launch_conv_tc(const void* in, const __nv_bfloat16* w, int w_fp16, const ConvGeom& g, const EpiParams& e, cudaStream_t st) {
+int launch_conv_tc(const void* in, const __nv_bfloat16* w, const ConvGeom& g, const EpiParams& e, cudaStream_t st) {
   TcParams p{};
   p.B = g.B; p.H = g.H; p.W = g.W; p.Cin = g.Cin; p.Cout = g.Cout;
   p.OH = g.OH; p.OW = g.OW; p.nphase = g.nphase; p.out_scale = g.out_scale; p.out_H = g.out_H; p.out_W = g.out_W;
@@ -534,8 +443,9 @@ int launch_conv_tc(const void* in, const __nv_bfloat16* w, int w_fp16, const Con
   p.tiles_x = ceil_div(g.OW, bw); p.tiles_y = ceil_div(g.OH, bh);
   const int bn = pick_block_n(g.Cout);
   p.tiles_n = g.Cout / bn;
-  (void)w_fp16;  // mixed bf16 x fp16 operands raise an illegal-instruction fault on sm_100a: both stay bf16
+  // (mixed bf16 x fp16 operands raise an illegal-instruction fault on sm_100a: both operands are bf16)
   p.idesc = make_idesc_bf16(kBlockM, bn, 0);
+  p.weight_taps = g.weight_taps > 0 ? g.weight_taps : 9;
   const int64_t total = (int64_t)p.tiles_x * p.tiles_y * g.B * p.tiles_n * g.nphase;
   if (total <= 0 || total > 0x7fffffff) {
     set_error("conv_tc: bad tile count %lld", (long long)total);

@@ -63,11 +63,36 @@ TapList upconv_taps(int py, int px) {
   return t;
 }
 
+// Plain Cin == 32 layers run on the halo kernel with vertically pair-packed input units; their producer
+// (the blur of the preceding up-conv) then writes that layout directly.
+bool layer_uses_pair_halo(l2i_generator* g, const StyledConvLayer& L, int B) {
+  if (g->dtype != L2I_BF16 || g->conv_impl == 1 || L.up || L.split || L.cin != 32 || L.w_pair == nullptr) return false;
+  ConvGeom geom{};
+  geom.B = B; geom.H = geom.W = L.res_in; geom.Cin = L.cin; geom.Cout = L.cout; geom.in_scale = 1; geom.weight_taps = 9;
+  geom.OH = geom.OW = L.res_in; geom.nphase = 1; geom.out_scale = 1; geom.out_H = geom.out_W = L.res_out;
+  EpiParams e{};
+  return conv_tc_halo_supported(geom, e);
+}
+
 int run_conv(l2i_generator* g, const StyledConvLayer& L, const void* in, const ConvGeom& geom, const EpiParams& e,
              cudaStream_t st) {
   if (g->dtype == L2I_F32) return launch_conv_simt<float>(in, L.w_f32, geom, e, st);
   const bool want_tc = g->conv_impl != 1;
-  if (want_tc && conv_tc_supported(geom, e)) return launch_conv_tc(in, L.w_bf16, g->weight_fp16, geom, e, st);
+  if (want_tc && !L.split && conv_tc_halo_supported(geom, e) && (geom.Cin != 32 || (L.w_pair != nullptr && geom.in_pair_packed)))
+    return launch_conv_tc_halo(in, geom.Cin == 32 ? L.w_pair : L.w_bf16, geom, e, st);
+  if (want_tc && conv_tc_supported(geom, e)) {
+    if (!L.split) return launch_conv_tc(in, L.w_bf16, geom, e, st);
+    // split-bf16 weights: every tap is issued twice, against the hi and the lo half of the weight tensor
+    ConvGeom g2 = geom;
+    g2.weight_taps = 18;
+    for (int ph = 0; ph < geom.nphase; ++ph) {
+      TapList& t = g2.taps[ph];
+      const int n = t.n;
+      for (int i = 0; i < n; ++i) { t.dy[n + i] = t.dy[i]; t.dx[n + i] = t.dx[i]; t.wtap[n + i] = (int8_t)(t.wtap[i] + 9); }
+      t.n = 2 * n;
+    }
+    return launch_conv_tc(in, L.w_bf16, g2, e, st);
+  }
   if (g->conv_impl == 2) {
     set_error("generator: L2I_CONV_IMPL=tc but layer %s is not supported by the tcgen05 kernel", L.name.c_str());
     return L2I_ERR_UNSUPPORTED;
@@ -105,6 +130,7 @@ extern "C" int l2i_generator_create(l2i_generator_t** out, int size, int style_d
     else if (!std::strcmp(env, "tc")) g->conv_impl = 2;
   }
 
+  if (const char* env = std::getenv("L2I_SPLIT_RES")) g->split_max_res = std::atoi(env);
   int rc = L2I_OK;
   auto fail = [&](int code) { l2i_generator_destroy(g); return code; };
   const int D = style_dim;
@@ -203,7 +229,9 @@ extern "C" int l2i_generator_create(l2i_generator_t** out, int size, int style_d
   // ---- packed weights ----
   for (auto& L : g->convs) {
     rc = dev_alloc(g, &L.w_f32, (int64_t)9 * L.cin * L.cout);
-    if (rc == L2I_OK && dtype == L2I_BF16) rc = dev_alloc(g, &L.w_bf16, (int64_t)9 * L.cin * L.cout);
+    L.split = dtype == L2I_BF16 && L.res_out <= g->split_max_res;
+    if (rc == L2I_OK && dtype == L2I_BF16) rc = dev_alloc(g, &L.w_bf16, (int64_t)(L.split ? 18 : 9) * L.cin * L.cout);
+    if (rc == L2I_OK && dtype == L2I_BF16 && L.cin == 32 && !L.up) rc = dev_alloc(g, &L.w_pair, (int64_t)12 * L.cout * 64);
     if (rc != L2I_OK) return fail(rc);
   }
 
@@ -282,7 +310,8 @@ extern "C" int l2i_generator_finalize(l2i_generator_t* g, void* stream) {
   for (auto& L : g->convs) {
     const float scale = 1.0f / std::sqrt((float)(L.cin * 9));
     L2I_TRY(launch_pack_conv_weight(L.w_f32, L.w_bf16, g->wsq_all + L.wsq_off, P(g, L.name + ".conv.weight"), L.cout,
-                                    L.cin, 9, scale, g->weight_fp16, st));
+                                    L.cin, 9, scale, L.split ? 1 : 0, st));
+    if (L.w_pair) L2I_TRY(launch_pack_pair_weight(L.w_pair, P(g, L.name + ".conv.weight"), L.cout, scale, st));
     L2I_TRY(launch_scale_copy(g->mod_w_all + (int64_t)L.s_off * D, P(g, L.name + ".conv.modulation.weight"),
                               (int64_t)L.cin * D, mod_scale, st));
     L2I_TRY(launch_scale_copy(g->mod_b_all + L.s_off, P(g, L.name + ".conv.modulation.bias"), L.cin, 1.f, st));
@@ -369,7 +398,7 @@ extern "C" int l2i_generator_forward(l2i_generator_t* g, const float* latent, in
     const float* s_next = next ? g->s_all + next->s_off : nullptr;
 
     ConvGeom geom{};
-    geom.B = B; geom.H = geom.W = L.res_in; geom.Cin = L.cin; geom.Cout = L.cout; geom.in_scale = 1;
+    geom.B = B; geom.H = geom.W = L.res_in; geom.Cin = L.cin; geom.Cout = L.cout; geom.in_scale = 1; geom.weight_taps = 9;
     const bool keep = g->training;
     if (keep) { g->convs[li].noise_ptr = nz; g->convs[li].noise_bs = nz_bs; }
     EpiParams e{};
@@ -390,10 +419,11 @@ extern "C" int l2i_generator_forward(l2i_generator_t* g, const float* latent, in
       g->seg_end(sg_c, st);
       auto* sg_b = g->seg_begin(L.name + "/blur_act", 1, 0.0, (px_t + px_out) * L.cout * es + px_out * 4.0, st);
       void* dst = g->act[cur ^ 1];
+      const bool pair_next = !f32 && next != nullptr && layer_uses_pair_halo(g, *next, B);
       if (f32) L2I_TRY(launch_blur_act<float, float>(dst, keep ? L.y_save : nullptr, tdst, B, L.res_out, L.res_out, L.cout, geom.out_H, geom.out_W, nz, nz_bs, nz_w,
-                                              P(g, L.name + ".activate.bias"), s_next, g->s_rows, g->fir, st));
+                                              P(g, L.name + ".activate.bias"), s_next, g->s_rows, g->fir, 0, st));
       else L2I_TRY(launch_blur_act<__nv_bfloat16, __half>(dst, keep ? L.y_save : nullptr, tdst, B, L.res_out, L.res_out, L.cout, geom.out_H, geom.out_W, nz, nz_bs,
-                                                  nz_w, P(g, L.name + ".activate.bias"), s_next, g->s_rows, g->fir, st));
+                                                  nz_w, P(g, L.name + ".activate.bias"), s_next, g->s_rows, g->fir, pair_next ? 1 : 0, st));
       g->seg_end(sg_b, st);
       cur ^= 1;
       g->conv_out[li] = g->act[cur];
@@ -404,6 +434,7 @@ extern "C" int l2i_generator_forward(l2i_generator_t* g, const float* latent, in
     const auto& R = g->rgbs[rgb_i];
     geom.OH = geom.OW = L.res_in; geom.nphase = 1; geom.out_scale = 1; geom.out_H = geom.out_W = L.res_out;
     geom.taps[0] = plain_taps();
+    geom.in_pair_packed = (!f32 && layer_uses_pair_halo(g, L, B)) ? 1 : 0;
     e.mode = 0;
     e.bias = P(g, L.name + ".activate.bias");
     e.noise = nz; e.noise_bs = nz_bs; e.noise_w = nz_w;

@@ -10,12 +10,15 @@ namespace l2i {
 
 // kernels implemented in the other translation units
 template <typename T> int launch_conv_simt(const void*, const float*, const ConvGeom&, const EpiParams&, cudaStream_t);
-int launch_conv_tc(const void* in, const __nv_bfloat16* w, int w_fp16, const ConvGeom& g, const EpiParams& e, cudaStream_t st);
+int launch_conv_tc(const void* in, const __nv_bfloat16* w, const ConvGeom& g, const EpiParams& e, cudaStream_t st);
 bool conv_tc_supported(const ConvGeom& g, const EpiParams& e);
 int conv_tc_block_n(const ConvGeom& g);
+bool conv_tc_halo_supported(const ConvGeom& g, const EpiParams& e);
+int launch_conv_tc_halo(const void* in, const __nv_bfloat16* w, const ConvGeom& g, const EpiParams& e, cudaStream_t st);
+int launch_pack_pair_weight(__nv_bfloat16* dst, const float* src, int Cout, float scale, cudaStream_t st);
 template <typename T, typename TIN>
 int launch_blur_act(void*, void*, const void*, int, int, int, int, int, int, const float*, int64_t, const float*,
-                    const float*, const float*, int64_t, const float*, cudaStream_t);
+                    const float*, const float*, int64_t, const float*, int, cudaStream_t);
 int launch_skip_combine(float*, const float*, int, const float*, const float*, int, int, int, const float*, cudaStream_t);
 template <typename T> int launch_const_input(void*, const float*, const float*, int64_t, int, int, int, cudaStream_t);
 int launch_demod(float*, int64_t, const float*, int64_t, const float*, const int64_t*, const int*, const int*, int, int, cudaStream_t);
@@ -41,7 +44,9 @@ struct StyledConvLayer {
   int s_off;   // offset of this layer's styles inside a row of s_all
   int d_off;   // offset of this layer's demod coefficients inside a row of d_all
   float* w_f32 = nullptr;            // [9][Cin][Cout]
-  __nv_bfloat16* w_bf16 = nullptr;   // [9][Cout][Cin]
+  __nv_bfloat16* w_bf16 = nullptr;   // [9][Cout][Cin], or [18][Cout][Cin] = bf16 hi halves then lo residuals (split)
+  __nv_bfloat16* w_pair = nullptr;   // Cin == 32 plain layers: [12][Cout][64] pair-packed tiles for the halo kernel
+  bool split = false;                // tensor-core path uses hi + lo weights (K doubled) to remove the weight rounding error
   float* w_f32_t = nullptr;          // [9][Cout][Cin] fp32, data-gradient convs (training only)
   // training state: saved activation y, saved raw up-conv output t, noise used by the last forward
   void* y_save = nullptr;
@@ -78,7 +83,7 @@ struct l2i_generator {
   float* fir2d_dev = nullptr;   // 4x4 FIR of the skip up-sampling, flipped, for the transposed op
   int* lat_seg = nullptr;       // [n_latent][1 + 2*3]: count, (row_start, row_count) x 3
   int conv_impl = 0;  // 0 auto, 1 simt, 2 tc
-  int weight_fp16 = 0;  // reserved: mixed bf16 x fp16 tcgen05 operands fault on sm_100a, weights stay bf16
+  int split_max_res = 64;  // layers with res_out <= this use split-bf16 weights on the tensor-core path
 
   std::unordered_map<std::string, Param> params;
   std::vector<StyledConvLayer> convs;

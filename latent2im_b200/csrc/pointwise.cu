@@ -27,11 +27,11 @@ struct alignas(sizeof(T) * VEC) TVec { T v[VEC]; };
 constexpr int kBlurRows = 32;
 
 template <typename T, typename TIN, int VEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 blur_act_kernel(T* __restrict__ out, T* __restrict__ y_out, const TIN* __restrict__ t, int B, int OH, int OW, int C, int TH, int TW,
                 const float* __restrict__ noise, int64_t noise_bs, const float* __restrict__ noise_w,
                 const float* __restrict__ bias, const float* __restrict__ s_next, int64_t s_next_bs,
-                float f0, float f1, float f2, float f3, int VP, int tiles_x, int tiles_y, int chunks) {
+                float f0, float f1, float f2, float f3, int VP, int tiles_x, int tiles_y, int chunks, int pair_pack) {
   using V = TVec<T, VEC>;
   using VIN = TVec<TIN, VEC>;
   constexpr float kSqrt2 = 1.4142135623730951f;
@@ -77,7 +77,7 @@ blur_act_kernel(T* __restrict__ out, T* __restrict__ y_out, const TIN* __restric
   hrow(Y0 + 1, h2);
   const float* nrow = noise != nullptr ? noise + (int64_t)b * noise_bs + X : nullptr;
   T* ob = out + ((int64_t)b * OH * OW + X) * C + c;
-#pragma unroll 2
+#pragma unroll 4
   for (int Y = Y0; Y < Y1; ++Y) {
     hrow(Y + 2, h3);
     const float nz = nrow != nullptr ? nw * __ldg(nrow + (int64_t)Y * OW) : 0.f;
@@ -94,7 +94,10 @@ blur_act_kernel(T* __restrict__ out, T* __restrict__ y_out, const TIN* __restric
       ov.v[k] = from_f32<T>(x * sn[k]);
       h0[k] = h1[k]; h1[k] = h2[k]; h2[k] = h3[k];
     }
-    *reinterpret_cast<V*>(ob + (int64_t)Y * OW * C) = ov;
+    if (pair_pack)  // [B][OH/2][OW][2][C]: the rows 2j, 2j+1 of a column sit side by side (128-byte units for C = 32)
+      *reinterpret_cast<V*>(out + ((((int64_t)b * (OH >> 1) + (Y >> 1)) * OW + X) * 2 + (Y & 1)) * C + c) = ov;
+    else
+      *reinterpret_cast<V*>(ob + (int64_t)Y * OW * C) = ov;
     if (y_out != nullptr) *reinterpret_cast<V*>(y_out + ((int64_t)b * OH * OW + X) * C + c + (int64_t)Y * OW * C) = yv;
   }
 }
@@ -102,8 +105,8 @@ blur_act_kernel(T* __restrict__ out, T* __restrict__ y_out, const TIN* __restric
 template <typename T, typename TIN>
 int launch_blur_act(void* out, void* y_out, const void* t, int B, int OH, int OW, int C, int TH, int TW, const float* noise,
                     int64_t noise_bs, const float* noise_w, const float* bias, const float* s_next,
-                    int64_t s_next_bs, const float* f, cudaStream_t st) {
-  constexpr int VEC = 16 / sizeof(T);
+                    int64_t s_next_bs, const float* f, int pair_pack, cudaStream_t st) {
+  constexpr int VEC = 4;  // 4 channels per thread (8-byte bf16 / 16-byte fp32 accesses) keeps the register windows small
   if (C % VEC != 0) {
     set_error("blur_act: C=%d not a multiple of %d", C, VEC);
     return L2I_ERR_UNSUPPORTED;
@@ -132,14 +135,14 @@ int launch_blur_act(void* out, void* y_out, const void* t, int B, int OH, int OW
   }
   blur_act_kernel<T, TIN, VEC><<<(unsigned)blocks, 256, 0, st>>>((T*)out, (T*)y_out, (const TIN*)t, B, OH, OW, C, TH, TW, noise, noise_bs,
                                                            noise_w, bias, s_next, s_next_bs, f[0], f[1], f[2], f[3], VP,
-                                                           tiles_x, tiles_y, chunks);
+                                                           tiles_x, tiles_y, chunks, pair_pack);
   return check_launch("blur_act");
 }
 template int launch_blur_act<float, float>(void*, void*, const void*, int, int, int, int, int, int, const float*, int64_t,
-                                           const float*, const float*, const float*, int64_t, const float*, cudaStream_t);
+                                           const float*, const float*, const float*, int64_t, const float*, int, cudaStream_t);
 template int launch_blur_act<__nv_bfloat16, __half>(void*, void*, const void*, int, int, int, int, int, int, const float*,
                                                     int64_t, const float*, const float*, const float*, int64_t,
-                                                    const float*, cudaStream_t);
+                                                    const float*, int, cudaStream_t);
 
 // ------------------------------------------------------------------------------------------------
 // skip_out[b,c,Y,X] = sum_p rgb_part[p][b][c][Y][X] + bias[c] + upsample2x(skip_in)[b,c,Y,X]
@@ -285,7 +288,7 @@ int launch_gather_latent(float* out, const float* in, int64_t bs, int64_t ls, in
 // wsq: [Cout][Cin] = sum_tap (scale*w)^2
 __global__ void pack_conv_weight_kernel(float* __restrict__ dst_f32, __nv_bfloat16* __restrict__ dst_bf16,
                                         float* __restrict__ wsq, const float* __restrict__ src, int Cout, int Cin,
-                                        int ntap, float scale, int as_fp16) {
+                                        int ntap, float scale, int split) {
   const int64_t total = (int64_t)Cout * Cin;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
@@ -298,8 +301,10 @@ __global__ void pack_conv_weight_kernel(float* __restrict__ dst_f32, __nv_bfloat
       if (dst_f32) dst_f32[((int64_t)t * Cin + ci) * Cout + co] = w;
       if (dst_bf16) {
         const int64_t o = ((int64_t)t * Cout + co) * Cin + ci;
-        if (as_fp16) reinterpret_cast<__half*>(dst_bf16)[o] = __float2half_rn(w);  // same 16-bit slot, fp16 encoding
-        else dst_bf16[o] = __float2bfloat16_rn(w);
+        const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+        dst_bf16[o] = hi;
+        // split mode: second half of the tensor holds the rounding residual, so hi + lo carries ~16 significand bits
+        if (split) dst_bf16[(int64_t)ntap * Cout * Cin + o] = __float2bfloat16_rn(w - __bfloat162float(hi));
       }
     }
     if (wsq) wsq[idx] = ss;
@@ -307,10 +312,10 @@ __global__ void pack_conv_weight_kernel(float* __restrict__ dst_f32, __nv_bfloat
 }
 
 int launch_pack_conv_weight(float* dst_f32, __nv_bfloat16* dst_bf16, float* wsq, const float* src, int Cout,
-                            int Cin, int ntap, float scale, int as_fp16, cudaStream_t st) {
+                            int Cin, int ntap, float scale, int split, cudaStream_t st) {
   const int64_t total = (int64_t)Cout * Cin;
   const int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)kNumSMs * 8);
-  pack_conv_weight_kernel<<<blocks, 256, 0, st>>>(dst_f32, dst_bf16, wsq, src, Cout, Cin, ntap, scale, as_fp16);
+  pack_conv_weight_kernel<<<blocks, 256, 0, st>>>(dst_f32, dst_bf16, wsq, src, Cout, Cin, ntap, scale, split);
   return check_launch("pack_conv_weight");
 }
 
