@@ -36,6 +36,11 @@ struct ConvGeom {
   int out_H, out_W;        // allocated dims of the output tensor
   int in_pair_packed;      // Cin == 32 input stored as [B][H/2][W][2][32]: vertical pixel pairs form 128-byte units
   int weight_taps;         // tap slices in the packed weight tensor: 9, or 18 when it holds bf16 hi + lo halves
+  // Composite up-conv (stride-2 transposed 3x3 conv + 4x4 blur folded into one 6x6 stride-2 kernel):
+  // run as a plain 3x3 conv at INPUT resolution whose GEMM N = 4 * up_cout enumerates (phase = py*2+px, co);
+  // column n lands at output pixel (2*oy + py, 2*ox + px), channel co.  0 = not composite.
+  int up_cout;
+  int out_pair_packed;     // composite only: write the Cout == 32 output as [B][H][2W][2][32] vertical pixel pairs
 };
 
 struct EpiParams {

@@ -31,6 +31,8 @@ struct TcParams {
   uint32_t a_bytes;               // bytes one A box load delivers (bw*bh*BLOCK_K*2)
   uint32_t idesc;                 // UMMA instruction descriptor (operand formats chosen on the host)
   int weight_taps;                // 9 or 18 tap slices in the weight tensor
+  int up_cout;                    // composite up-conv: real Cout (GEMM N = 4 * up_cout = (phase, co)); 0 otherwise
+  int pair_out;                   // composite: pair-packed output for the following Cin == 32 halo layer
   EpiParams e;
 };
 
@@ -183,6 +185,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const float nw = (e.noise != nullptr && e.noise_w != nullptr) ? __ldg(e.noise_w) * kSqrt2 : 0.f;
     const int64_t plane = (int64_t)p.out_H * p.out_W;
     const int lx = row % p.bw, ly = row / p.bw;
+    const bool comp = p.up_cout > 0;
     uint32_t acc_phase = 0;
     int staged_key = -1;
     int it = 0;
@@ -192,7 +195,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       decode(tile, ph, x0, y0, b, nt);
       const int ox = x0 + lx, oy = y0 + ly;
       const bool valid = ly < p.bh && ox < p.OW && oy < p.OH;
-      const int Y = oy * p.out_scale + (ph >> 1), X = ox * p.out_scale + (ph & 1);
+      // composite: (Y, X) is the top-left of this input pixel's 2x2 output quad, the phase comes from the column
+      const int Y = comp ? 2 * oy : oy * p.out_scale + (ph >> 1), X = comp ? 2 * ox : ox * p.out_scale + (ph & 1);
 
       // ---- per-(sample, N-tile) epilogue vectors -> shared memory (rarely changes between tiles) ----
       const int key = b * p.tiles_n + nt;
@@ -200,7 +204,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         group_sync(group);  // everyone is done with the previous vectors
         const int co0 = nt * BLOCK_N;
         for (int j = gtid; j < BLOCK_N; j += 128) {
-          const int co = co0 + j;
+          const int co = comp ? (co0 + j) % p.up_cout : co0 + j;
           const float d = e.demod != nullptr ? __ldg(e.demod + (int64_t)b * e.demod_bs + co) : 1.f;
           if (e.mode == 0) {
             s_d[j] = d * kSqrt2;
@@ -218,9 +222,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
 
       // ---- issue every global load of this tile before waiting for the accumulator ----
-      float nz = 0.f;
-      if (e.mode == 0 && e.noise != nullptr && valid)
-        nz = nw * __ldg(e.noise + (int64_t)b * e.noise_bs + (int64_t)Y * p.out_W + X);
+      float nz = 0.f, nz1 = 0.f, nz2 = 0.f, nz3 = 0.f;
+      if (e.mode == 0 && e.noise != nullptr && valid) {
+        const float* np = e.noise + (int64_t)b * e.noise_bs + (int64_t)Y * p.out_W + X;
+        nz = nw * __ldg(np);
+        if (comp) { nz1 = nw * __ldg(np + 1); nz2 = nw * __ldg(np + p.out_W); nz3 = nw * __ldg(np + p.out_W + 1); }
+      }
       float up[3] = {0.f, 0.f, 0.f};
       if (e.mode == 0 && e.fused_skip && valid) {
 #pragma unroll
@@ -231,10 +238,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       }
       __nv_bfloat16* outp = nullptr;
-      if (valid && e.out != nullptr && (e.mode == 1 || e.s_next != nullptr))
+      if (!comp && valid && e.out != nullptr && (e.mode == 1 || e.s_next != nullptr))
         outp = (__nv_bfloat16*)e.out + (((int64_t)b * p.out_H + Y) * p.out_W + X) * p.Cout + nt * BLOCK_N;
       __nv_bfloat16* yp = nullptr;
-      if (valid && e.mode == 0 && e.y_out != nullptr)
+      if (!comp && valid && e.mode == 0 && e.y_out != nullptr)
         yp = (__nv_bfloat16*)e.y_out + (((int64_t)b * p.out_H + Y) * p.out_W + X) * p.Cout + nt * BLOCK_N;
       float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
 
@@ -245,6 +252,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + c0, v);
+        float nzc = nz;
+        __nv_bfloat16* outc = outp != nullptr ? outp + c0 : nullptr;
+        __nv_bfloat16* yc = yp != nullptr ? yp + c0 : nullptr;
+        if (comp) {  // this 32-column chunk belongs to one output phase (up_cout % 32 == 0)
+          const int n = nt * BLOCK_N + c0;
+          const int phc = n / p.up_cout, cb = n - phc * p.up_cout;
+          nzc = phc == 0 ? nz : (phc == 1 ? nz1 : (phc == 2 ? nz2 : nz3));
+          if (valid) {
+            const int Xc = X + (phc & 1);
+            const int64_t pix = ((int64_t)b * p.out_H + Y + (phc >> 1)) * p.out_W + Xc;
+            const int64_t opix = p.pair_out ? ((((int64_t)b * (p.out_H >> 1) + oy) * p.out_W + Xc) * 2 + (phc >> 1)) : pix;
+            if (e.out != nullptr) outc = (__nv_bfloat16*)e.out + opix * p.up_cout + cb;
+            if (e.y_out != nullptr) yc = (__nv_bfloat16*)e.y_out + pix * p.up_cout + cb;
+          }
+        }
         tmem_ld_wait();
         uint32_t packed[16];
         uint32_t ypacked[16];
@@ -264,7 +286,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const float a0[4] = {w0.x, w0.y, w0.z, w0.w}, a1[4] = {w1.x, w1.y, w1.z, w1.w}, a2[4] = {w2.x, w2.y, w2.z, w2.w};
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
-              float x = fmaf(__uint_as_float(v[j4 + h]), dd[h], bb[h] + nz);
+              float x = fmaf(__uint_as_float(v[j4 + h]), dd[h], bb[h] + nzc);
               x = fmaxf(x, 0.2f * x);  // leaky relu (the sqrt(2) gain is folded into dd / bb / nz)
               rgb0 = fmaf(a0[h], x, rgb0);
               rgb1 = fmaf(a1[h], x, rgb1);
@@ -291,13 +313,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             packed[(j4 >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p1);
           }
         }
-        if (yp != nullptr) {
-          uint4* dst = reinterpret_cast<uint4*>(yp + c0);
+        if (yc != nullptr) {
+          uint4* dst = reinterpret_cast<uint4*>(yc);
 #pragma unroll
           for (int k = 0; k < 4; ++k) dst[k] = make_uint4(ypacked[4 * k], ypacked[4 * k + 1], ypacked[4 * k + 2], ypacked[4 * k + 3]);
         }
-        if (outp != nullptr) {
-          uint4* dst = reinterpret_cast<uint4*>(outp + c0);
+        if (outc != nullptr) {
+          uint4* dst = reinterpret_cast<uint4*>(outc);
 #pragma unroll
           for (int k = 0; k < 4; ++k) dst[k] = make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
         }
@@ -446,6 +468,13 @@ int launch_conv_tc(const void* in, const __nv_bfloat16* w, const ConvGeom& g, co
   // (mixed bf16 x fp16 operands raise an illegal-instruction fault on sm_100a: both operands are bf16)
   p.idesc = make_idesc_bf16(kBlockM, bn, 0);
   p.weight_taps = g.weight_taps > 0 ? g.weight_taps : 9;
+  p.up_cout = g.up_cout;
+  p.pair_out = g.out_pair_packed;
+  if (g.up_cout > 0 && (g.Cout != 4 * g.up_cout || g.up_cout % 32 != 0 || g.nphase != 1 || e.mode != 0 || e.wr != nullptr ||
+                        (g.out_pair_packed && g.up_cout != 32))) {
+    set_error("conv_tc: bad composite up-conv configuration (Cout=%d up_cout=%d)", g.Cout, g.up_cout);
+    return L2I_ERR_INVALID_ARG;
+  }
   const int64_t total = (int64_t)p.tiles_x * p.tiles_y * g.B * p.tiles_n * g.nphase;
   if (total <= 0 || total > 0x7fffffff) {
     set_error("conv_tc: bad tile count %lld", (long long)total);

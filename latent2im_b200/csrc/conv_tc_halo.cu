@@ -35,6 +35,8 @@ struct HaloParams {
   int ntaps, nacc, nwtiles;
   HaloTap taps[16];
   int out_mode;            // 0 plain: (Y,X)=(oy,ox); 1 up: (2oy+py, 2ox+px), acc = py*2+px; 2 pair: (2oy+acc, ox)
+                           // 3 composite up-conv: one accumulator of 4*Cout columns, column chunk = phase (py*2+px)
+  int pair_out;            // composite: write [B][H][2W][2][32] vertical pixel pairs for the following Cin == 32 layer
   int out_H, out_W;
   int tiles_x, tiles_y, total_tiles;
   uint32_t idesc;
@@ -73,15 +75,18 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, u
       : "memory");
 }
 
-// N = Cout (32 or 64), STAGES = A halo stages, PAIR = Cin 32 pair-packed units (5-D A map)
-template <int N, int STAGES, int NACC, bool PAIR>
+// N = GEMM N (Cout, or 4 * Cout for the composite up-conv), STAGES = A halo stages, PAIR = Cin 32 pair-packed
+// units, COMP = composite up-conv (N = 4 phases x 32 channels, fused blur: SURVEY 0.6b)
+template <int N, int STAGES, int NACC, bool PAIR, bool COMP>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ HaloParams p) {
   constexpr int kWTileBytes = N * 128;
   constexpr int kTmemCols = kGroups * NACC * N;
   static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM budget");
-  constexpr int kEpiFloats = 6 * N;
+  constexpr int CO = COMP ? N / 4 : N;   // distinct output channels whose epilogue vectors are staged
+  constexpr int kEpiFloats = 6 * CO;
+  static_assert(!COMP || (CO == 32 && NACC == 1), "composite variant: 4 phases x 32 channels in one accumulator");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -181,9 +186,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int gtid = threadIdx.x - (128 + group * 128);
     float* sp = epi_smem + group * kEpiFloats;
     float* s_d = sp;
-    float* s_b = sp + N;
-    float* s_n = sp + 2 * N;
-    float* s_w = sp + 3 * N;
+    float* s_b = sp + CO;
+    float* s_n = sp + 2 * CO;
+    float* s_w = sp + 3 * CO;
     constexpr float kSqrt2 = 1.4142135623730951f;
     const float nw = (e.noise != nullptr && e.noise_w != nullptr) ? __ldg(e.noise_w) * kSqrt2 : 0.f;
     const int64_t plane = (int64_t)p.out_H * p.out_W;
@@ -200,14 +205,14 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
       if (b != staged_b) {
         halo_group_sync(group);
-        for (int j = gtid; j < N; j += 128) {
+        for (int j = gtid; j < CO; j += 128) {
           const float d = e.demod != nullptr ? __ldg(e.demod + (int64_t)b * e.demod_bs + j) : 1.f;
           if (e.mode == 0) {
             s_d[j] = d * kSqrt2;
             s_b[j] = __ldg(e.bias + j) * kSqrt2;
             s_n[j] = e.s_next ? __ldg(e.s_next + (int64_t)b * e.s_next_bs + j) : 1.f;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) s_w[c * N + j] = e.wr ? __ldg(e.wr + (int64_t)b * e.wr_bs + c * p.Cout + j) : 0.f;
+            for (int c = 0; c < 3; ++c) s_w[c * CO + j] = e.wr ? __ldg(e.wr + (int64_t)b * e.wr_bs + c * p.Cout + j) : 0.f;
           } else {
             s_d[j] = d;
           }
@@ -220,15 +225,23 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int Ys[NACC], Xs[NACC];
       bool ok[NACC];
       float nz[NACC], up[NACC][3];
+      float nzq[4] = {0.f, 0.f, 0.f, 0.f};   // composite: noise of the 2x2 output quad of this input pixel
+      if (COMP && in_grid && e.noise != nullptr) {
+        const float* np = e.noise + (int64_t)b * e.noise_bs + (int64_t)(2 * oy) * p.out_W + 2 * ox;
+        const float2 n01 = __ldg(reinterpret_cast<const float2*>(np));
+        const float2 n23 = __ldg(reinterpret_cast<const float2*>(np + p.out_W));
+        nzq[0] = nw * n01.x; nzq[1] = nw * n01.y; nzq[2] = nw * n23.x; nzq[3] = nw * n23.y;
+      }
 #pragma unroll
       for (int a = 0; a < NACC; ++a) {
-        if (p.out_mode == 1) { Ys[a] = 2 * oy + (a >> 1); Xs[a] = 2 * ox + (a & 1); }
+        if (COMP) { Ys[a] = 2 * oy; Xs[a] = 2 * ox; }
+        else if (p.out_mode == 1) { Ys[a] = 2 * oy + (a >> 1); Xs[a] = 2 * ox + (a & 1); }
         else if (p.out_mode == 2) { Ys[a] = 2 * oy + a; Xs[a] = ox; }
         else { Ys[a] = oy; Xs[a] = ox; }
         ok[a] = in_grid && Ys[a] < p.out_H && Xs[a] < p.out_W;
         nz[a] = 0.f;
         up[a][0] = up[a][1] = up[a][2] = 0.f;
-        if (e.mode == 0 && ok[a]) {
+        if (!COMP && e.mode == 0 && ok[a]) {
           if (e.noise != nullptr) nz[a] = nw * __ldg(e.noise + (int64_t)b * e.noise_bs + (int64_t)Ys[a] * p.out_W + Xs[a]);
           if (e.fused_skip) {
 #pragma unroll
@@ -248,31 +261,47 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((group * NACC + a) * N);
         const int64_t pix = ((int64_t)b * p.out_H + Ys[a]) * p.out_W + Xs[a];
         __nv_bfloat16* outp = nullptr;
-        if (ok[a] && e.out != nullptr && (e.mode == 1 || e.s_next != nullptr)) outp = (__nv_bfloat16*)e.out + pix * p.Cout;
+        if (!COMP && ok[a] && e.out != nullptr && (e.mode == 1 || e.s_next != nullptr)) outp = (__nv_bfloat16*)e.out + pix * p.Cout;
         __nv_bfloat16* yp = nullptr;
-        if (ok[a] && e.mode == 0 && e.y_out != nullptr) yp = (__nv_bfloat16*)e.y_out + pix * p.Cout;
+        if (!COMP && ok[a] && e.mode == 0 && e.y_out != nullptr) yp = (__nv_bfloat16*)e.y_out + pix * p.Cout;
         float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
 #pragma unroll 1
         for (int c0 = 0; c0 < N; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(taddr + c0, v);
+          const int cs = COMP ? 0 : c0;        // offset of this chunk's channels in the staged vectors
+          float nzc = nz[a];
+          __nv_bfloat16* outc = outp != nullptr ? outp + c0 : nullptr;
+          __nv_bfloat16* yc = yp != nullptr ? yp + c0 : nullptr;
+          if (COMP) {                          // chunk = output phase
+            const int phc = c0 >> 5;
+            nzc = phc == 0 ? nzq[0] : (phc == 1 ? nzq[1] : (phc == 2 ? nzq[2] : nzq[3]));
+            outc = yc = nullptr;
+            if (ok[a]) {
+              const int Xc = Xs[a] + (phc & 1);
+              const int64_t pixc = ((int64_t)b * p.out_H + Ys[a] + (phc >> 1)) * p.out_W + Xc;
+              const int64_t opix = p.pair_out ? ((((int64_t)b * (p.out_H >> 1) + oy) * p.out_W + Xc) * 2 + (phc >> 1)) : pixc;
+              if (e.out != nullptr) outc = (__nv_bfloat16*)e.out + opix * CO;
+              if (e.y_out != nullptr) yc = (__nv_bfloat16*)e.y_out + pixc * CO;
+            }
+          }
           tmem_ld_wait();
           uint32_t packed[16], ypacked[16];
 #pragma unroll
           for (int j4 = 0; j4 < 32; j4 += 4) {
-            const float4 d4 = *reinterpret_cast<const float4*>(s_d + c0 + j4);
+            const float4 d4 = *reinterpret_cast<const float4*>(s_d + cs + j4);
             float o[4], yy[4] = {0.f, 0.f, 0.f, 0.f};
             if (e.mode == 0) {
-              const float4 b4 = *reinterpret_cast<const float4*>(s_b + c0 + j4);
-              const float4 n4 = *reinterpret_cast<const float4*>(s_n + c0 + j4);
-              const float4 w0 = *reinterpret_cast<const float4*>(s_w + c0 + j4);
-              const float4 w1 = *reinterpret_cast<const float4*>(s_w + N + c0 + j4);
-              const float4 w2 = *reinterpret_cast<const float4*>(s_w + 2 * N + c0 + j4);
+              const float4 b4 = *reinterpret_cast<const float4*>(s_b + cs + j4);
+              const float4 n4 = *reinterpret_cast<const float4*>(s_n + cs + j4);
+              const float4 w0 = *reinterpret_cast<const float4*>(s_w + cs + j4);
+              const float4 w1 = *reinterpret_cast<const float4*>(s_w + CO + cs + j4);
+              const float4 w2 = *reinterpret_cast<const float4*>(s_w + 2 * CO + cs + j4);
               const float dd[4] = {d4.x, d4.y, d4.z, d4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w}, nn[4] = {n4.x, n4.y, n4.z, n4.w};
               const float a0[4] = {w0.x, w0.y, w0.z, w0.w}, a1[4] = {w1.x, w1.y, w1.z, w1.w}, a2[4] = {w2.x, w2.y, w2.z, w2.w};
 #pragma unroll
               for (int h = 0; h < 4; ++h) {
-                float x = fmaf(__uint_as_float(v[j4 + h]), dd[h], bb[h] + nz[a]);
+                float x = fmaf(__uint_as_float(v[j4 + h]), dd[h], bb[h] + nzc);
                 x = fmaxf(x, 0.2f * x);
                 rgb0 = fmaf(a0[h], x, rgb0);
                 rgb1 = fmaf(a1[h], x, rgb1);
@@ -299,13 +328,13 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               packed[(j4 >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p1);
             }
           }
-          if (yp != nullptr) {
-            uint4* dst = reinterpret_cast<uint4*>(yp + c0);
+          if (yc != nullptr) {
+            uint4* dst = reinterpret_cast<uint4*>(yc);
 #pragma unroll
             for (int k = 0; k < 4; ++k) dst[k] = make_uint4(ypacked[4 * k], ypacked[4 * k + 1], ypacked[4 * k + 2], ypacked[4 * k + 3]);
           }
-          if (outp != nullptr) {
-            uint4* dst = reinterpret_cast<uint4*>(outp + c0);
+          if (outc != nullptr) {
+            uint4* dst = reinterpret_cast<uint4*>(outc);
 #pragma unroll
             for (int k = 0; k < 4; ++k) dst[k] = make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
           }
@@ -335,15 +364,15 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
-template <int N, int STAGES, int NACC, bool PAIR>
+template <int N, int STAGES, int NACC, bool PAIR, bool COMP = false>
 int launch_halo_variant(const CUtensorMap& ta, const CUtensorMap& tw, const HaloParams& p, cudaStream_t st) {
   const int wbytes = ((p.nwtiles * N * 128) + 1023) & ~1023;
-  const int smem = STAGES * kHaloBytes + wbytes + kGroups * 6 * N * 4 + 256 + 1024;
+  const int smem = STAGES * kHaloBytes + wbytes + kGroups * 6 * (COMP ? N / 4 : N) * 4 + 256 + 1024;
   if (smem > 227 * 1024) {
     set_error("conv_tc_halo: shared memory budget exceeded (%d bytes)", smem);
     return L2I_ERR_UNSUPPORTED;
   }
-  auto kern = conv_tc_halo_kernel<N, STAGES, NACC, PAIR>;
+  auto kern = conv_tc_halo_kernel<N, STAGES, NACC, PAIR, COMP>;
   static int attr_smem = 0;
   if (attr_smem < smem) {
     L2I_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -354,26 +383,27 @@ int launch_halo_variant(const CUtensorMap& ta, const CUtensorMap& tw, const Halo
   return check_launch("conv_tc_halo");
 }
 
-int g_halo_enabled = -1, g_halo_boff = 0, g_halo_mask = 7;
+int g_halo_enabled = -1, g_halo_boff = 0, g_halo_mask = 15;
 
 }  // namespace
 
 // Which layers this kernel takes: plain 64->64 / 64->32 ... with Cin == 64, Cout in {32, 64}; the
 // stride-2 transposed conv with Cin == 64; and Cin == 32 -> 32 plain through the pair-packed view.
 bool conv_tc_halo_supported(const ConvGeom& g, const EpiParams& e) {
-  (void)e;
   if (g_halo_enabled < 0) {
     const char* env = std::getenv("L2I_HALO");
     g_halo_enabled = (env != nullptr && env[0] == '0') ? 0 : 1;
     const char* bo = std::getenv("L2I_HALO_BASE_OFFSET");
     if (bo != nullptr) g_halo_boff = bo[0] != '0';
-    const char* mk = std::getenv("L2I_HALO_MASK");   // bit 0 plain Cin=64, bit 1 up-conv, bit 2 pair-packed Cin=32
+    const char* mk = std::getenv("L2I_HALO_MASK");   // bit 0 plain Cin=64, bit 1 up-conv, bit 2 pair-packed Cin=32, bit 3 composite up-conv
     if (mk != nullptr) g_halo_mask = std::atoi(mk);
   }
   if (!g_halo_enabled || !tmap_available()) return false;
   if (g.in_scale != 1 || g.weight_taps != 9) return false;
-  if (!(g.Cout == 32 || g.Cout == 64)) return false;
   if (g.H < 16 || g.W < 16) return false;
+  if (g.up_cout > 0)   // composite up-conv 64 -> 32: GEMM N = 128, weights (9 x 16 KB) resident
+    return g.nphase == 1 && g.Cin == 64 && g.up_cout == 32 && g.Cout == 128 && e.mode == 0 && e.wr == nullptr && (g_halo_mask & 8) != 0;
+  if (!(g.Cout == 32 || g.Cout == 64)) return false;
   if (g.nphase == 1 && g.Cin == 64) return (g_halo_mask & 1) != 0;
   if (g.nphase == 4 && g.Cin == 64 && g.Cout == 32) return (g_halo_mask & 2) != 0;   // 4 accumulators x 32 columns x 4 groups = 512 TMEM columns
   if (g.nphase == 1 && g.Cin == 32 && g.Cout == 32 && (g.H % 2 == 0)) return (g_halo_mask & 4) != 0;  // caller provides pair-packed input
@@ -384,6 +414,7 @@ bool conv_tc_halo_supported(const ConvGeom& g, const EpiParams& e) {
 int launch_conv_tc_halo(const void* in, const __nv_bfloat16* w, const ConvGeom& g, const EpiParams& e, cudaStream_t st) {
   HaloParams p{};
   p.B = g.B; p.Cout = g.Cout; p.out_H = g.out_H; p.out_W = g.out_W; p.e = e;
+  p.pair_out = g.out_pair_packed;
   p.base_offset_mode = g_halo_boff;
   p.idesc = make_idesc_bf16(128, g.Cout, 0);
   const bool pair = g.Cin == 32;
@@ -396,7 +427,11 @@ int launch_conv_tc_halo(const void* in, const __nv_bfloat16* w, const ConvGeom& 
     const uint32_t box[4] = {64, kHaloW, kHaloH, 1};
     L2I_TRY(make_tmap(&ta, in, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
   }
-  if (g.nphase == 4) {  // stride-2 transposed conv: all four output phases from one halo tile
+  if (g.up_cout > 0) {  // composite up-conv: a plain 3x3 conv at input resolution with N = 4 * Cout
+    p.out_mode = 3; p.nacc = 1; p.nwtiles = 9; p.ntaps = 0;
+    p.OUH = g.OH; p.OUW = g.OW;
+    for (int t = 0; t < g.taps[0].n; ++t) p.taps[p.ntaps++] = HaloTap{g.taps[0].dy[t], g.taps[0].dx[t], g.taps[0].wtap[t], 0};
+  } else if (g.nphase == 4) {  // stride-2 transposed conv: all four output phases from one halo tile
     p.out_mode = 1; p.nacc = 4; p.nwtiles = 9; p.ntaps = 0;
     p.OUH = g.OH; p.OUW = g.OW;
     for (int ph = 0; ph < 4; ++ph)
@@ -425,6 +460,7 @@ int launch_conv_tc_halo(const void* in, const __nv_bfloat16* w, const ConvGeom& 
   const int64_t total = (int64_t)p.tiles_x * p.tiles_y * g.B;
   if (total <= 0 || total > 0x7fffffff) { set_error("conv_tc_halo: bad tile count"); return L2I_ERR_INVALID_ARG; }
   p.total_tiles = (int)total;
+  if (g.up_cout > 0) return launch_halo_variant<128, 2, 1, false, true>(ta, tw, p, st);
   if (g.nphase == 4) return launch_halo_variant<32, 4, 4, false>(ta, tw, p, st);
   if (pair) return launch_halo_variant<32, 4, 2, true>(ta, tw, p, st);
   if (g.Cout == 64) return launch_halo_variant<64, 3, 1, false>(ta, tw, p, st);

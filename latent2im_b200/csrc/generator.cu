@@ -131,6 +131,7 @@ extern "C" int l2i_generator_create(l2i_generator_t** out, int size, int style_d
   }
 
   if (const char* env = std::getenv("L2I_SPLIT_RES")) g->split_max_res = std::atoi(env);
+  if (const char* env = std::getenv("L2I_COMPOSITE_RES")) g->composite_min_res = std::atoi(env);
   int rc = L2I_OK;
   auto fail = [&](int code) { l2i_generator_destroy(g); return code; };
   const int D = style_dim;
@@ -232,6 +233,9 @@ extern "C" int l2i_generator_create(l2i_generator_t** out, int size, int style_d
     L.split = dtype == L2I_BF16 && L.res_out <= g->split_max_res;
     if (rc == L2I_OK && dtype == L2I_BF16) rc = dev_alloc(g, &L.w_bf16, (int64_t)(L.split ? 18 : 9) * L.cin * L.cout);
     if (rc == L2I_OK && dtype == L2I_BF16 && L.cin == 32 && !L.up) rc = dev_alloc(g, &L.w_pair, (int64_t)12 * L.cout * 64);
+    L.composite = dtype == L2I_BF16 && L.up && g->conv_impl != 1 && L.res_out >= g->composite_min_res && L.cout % 32 == 0 &&
+                  L.cin % 64 == 0;
+    if (rc == L2I_OK && L.composite) rc = dev_alloc(g, &L.w_comp, (int64_t)36 * L.cin * L.cout);
     if (rc != L2I_OK) return fail(rc);
   }
 
@@ -312,6 +316,7 @@ extern "C" int l2i_generator_finalize(l2i_generator_t* g, void* stream) {
     L2I_TRY(launch_pack_conv_weight(L.w_f32, L.w_bf16, g->wsq_all + L.wsq_off, P(g, L.name + ".conv.weight"), L.cout,
                                     L.cin, 9, scale, L.split ? 1 : 0, st));
     if (L.w_pair) L2I_TRY(launch_pack_pair_weight(L.w_pair, P(g, L.name + ".conv.weight"), L.cout, scale, st));
+    if (L.w_comp) L2I_TRY(launch_pack_composite_weight(L.w_comp, P(g, L.name + ".conv.weight"), L.cout, L.cin, scale, g->fir, st));
     L2I_TRY(launch_scale_copy(g->mod_w_all + (int64_t)L.s_off * D, P(g, L.name + ".conv.modulation.weight"),
                               (int64_t)L.cin * D, mod_scale, st));
     L2I_TRY(launch_scale_copy(g->mod_b_all + L.s_off, P(g, L.name + ".conv.modulation.bias"), L.cin, 1.f, st));
@@ -405,6 +410,29 @@ extern "C" int l2i_generator_forward(l2i_generator_t* g, const float* latent, in
     e.demod = g->d_all + L.d_off; e.demod_bs = g->d_rows;
     for (int i = 0; i < 4; ++i) e.fir[i] = g->fir[i];
 
+    if (L.up && L.composite && !keep) {
+      // transposed conv + blur + noise + bias + lrelu + next-style scale in ONE kernel: a 3x3 conv at input
+      // resolution with N = 4 phases x Cout (composite 6x6 stride-2 kernel), no (2H+1)^2 intermediate
+      geom.OH = geom.OW = L.res_in; geom.nphase = 1; geom.out_scale = 1; geom.out_H = geom.out_W = L.res_out;
+      geom.taps[0] = plain_taps();
+      geom.Cout = 4 * L.cout; geom.up_cout = L.cout;
+      geom.out_pair_packed = (next != nullptr && layer_uses_pair_halo(g, *next, B)) ? 1 : 0;
+      e.mode = 0;
+      e.bias = P(g, L.name + ".activate.bias");
+      e.noise = nz; e.noise_bs = nz_bs; e.noise_w = nz_w;
+      e.s_next = s_next; e.s_next_bs = g->s_rows;
+      e.out = g->act[cur ^ 1];
+      const double px_in = (double)B * L.res_in * L.res_in, px_out = (double)B * L.res_out * L.res_out;
+      auto* sg_c = g->seg_begin(L.name + "/upconv+blur_act", 0, 2.0 * 9 * L.cin * L.cout * px_in,
+                                (px_in * L.cin + px_out * L.cout) * es + px_out * 4.0, st);
+      if (conv_tc_halo_supported(geom, e)) L2I_TRY(launch_conv_tc_halo(g->act[cur], L.w_comp, geom, e, st));
+      else if (conv_tc_supported(geom, e)) L2I_TRY(launch_conv_tc(g->act[cur], L.w_comp, geom, e, st));
+      else { set_error("generator: composite up-conv of %s is not supported by the tcgen05 kernels", L.name.c_str()); return L2I_ERR_UNSUPPORTED; }
+      g->seg_end(sg_c, st);
+      cur ^= 1;
+      g->conv_out[li] = g->act[cur];
+      continue;
+    }
     if (L.up) {
       geom.OH = geom.OW = L.res_in + 1; geom.nphase = 4; geom.out_scale = 2;
       geom.out_H = geom.out_W = 2 * L.res_in + 2;

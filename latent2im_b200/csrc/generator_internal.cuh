@@ -16,6 +16,7 @@ int conv_tc_block_n(const ConvGeom& g);
 bool conv_tc_halo_supported(const ConvGeom& g, const EpiParams& e);
 int launch_conv_tc_halo(const void* in, const __nv_bfloat16* w, const ConvGeom& g, const EpiParams& e, cudaStream_t st);
 int launch_pack_pair_weight(__nv_bfloat16* dst, const float* src, int Cout, float scale, cudaStream_t st);
+int launch_pack_composite_weight(__nv_bfloat16* dst, const float* src, int Cout, int Cin, float scale, const float* fir, cudaStream_t st);
 template <typename T, typename TIN>
 int launch_blur_act(void*, void*, const void*, int, int, int, int, int, int, const float*, int64_t, const float*,
                     const float*, const float*, int64_t, const float*, int, cudaStream_t);
@@ -46,6 +47,8 @@ struct StyledConvLayer {
   float* w_f32 = nullptr;            // [9][Cin][Cout]
   __nv_bfloat16* w_bf16 = nullptr;   // [9][Cout][Cin], or [18][Cout][Cin] = bf16 hi halves then lo residuals (split)
   __nv_bfloat16* w_pair = nullptr;   // Cin == 32 plain layers: [12][Cout][64] pair-packed tiles for the halo kernel
+  __nv_bfloat16* w_comp = nullptr;   // composite up-conv (transposed conv + blur folded): [9][4*Cout][Cin], rows (phase, co)
+  bool composite = false;            // inference forward of this up layer runs the composite kernel (no t intermediate)
   bool split = false;                // tensor-core path uses hi + lo weights (K doubled) to remove the weight rounding error
   float* w_f32_t = nullptr;          // [9][Cout][Cin] fp32, data-gradient convs (training only)
   // training state: saved activation y, saved raw up-conv output t, noise used by the last forward
@@ -84,6 +87,7 @@ struct l2i_generator {
   int* lat_seg = nullptr;       // [n_latent][1 + 2*3]: count, (row_start, row_count) x 3
   int conv_impl = 0;  // 0 auto, 1 simt, 2 tc
   int split_max_res = 64;  // layers with res_out <= this use split-bf16 weights on the tensor-core path
+  int composite_min_res = 256;  // up layers with res_out >= this fold the blur into the conv weights (bf16 inference path)
 
   std::unordered_map<std::string, Param> params;
   std::vector<StyledConvLayer> convs;

@@ -319,6 +319,46 @@ int launch_pack_conv_weight(float* dst_f32, __nv_bfloat16* dst_bf16, float* wsq,
   return check_launch("pack_conv_weight");
 }
 
+// Composite up-conv weights: conv_transpose2d(3x3, stride 2) followed by the 4x4 FIR blur (pad (1,1)) is one
+// stride-2 transposed conv with a 6x6 kernel; per output phase (py, px) it is a 3x3 conv over the input pixels
+// (y + dy, x + dx), dy, dx in {-1, 0, 1}:
+//   Wc[py,px][dy,dx] = sum_{i,kh : py + i - 1 - kh = 2 dy} sum_{j,kw : px + j - 1 - kw = 2 dx} f[i] f[j] W[kh,kw]
+// (t[2y+kh] += W[kh] x[y]; out[Y] = sum_i f[i] t[Y + i - 1]).  dst: [tap = (dy+1)*3 + (dx+1)][(py*2+px)*Cout + co][Cin] bf16.
+__global__ void pack_composite_weight_kernel(__nv_bfloat16* __restrict__ dst, const float* __restrict__ src, int Cout,
+                                             int Cin, float scale, float f0, float f1, float f2, float f3) {
+  const float f[4] = {f0, f1, f2, f3};
+  const int64_t total = (int64_t)9 * 4 * Cout * Cin;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(idx % Cin);
+    const int row = (int)((idx / Cin) % (4 * Cout));
+    const int tap = (int)(idx / ((int64_t)Cin * 4 * Cout));
+    const int co = row % Cout, ph = row / Cout;
+    const int py = ph >> 1, px = ph & 1, dy = tap / 3 - 1, dx = tap % 3 - 1;
+    const float* w = src + ((int64_t)co * Cin + ci) * 9;
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kh = py + i - 1 - 2 * dy;
+      if (kh < 0 || kh > 2) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int kw = px + j - 1 - 2 * dx;
+        if (kw < 0 || kw > 2) continue;
+        acc = fmaf(f[i] * f[j], w[kh * 3 + kw], acc);
+      }
+    }
+    dst[idx] = __float2bfloat16_rn(acc * scale);
+  }
+}
+
+int launch_pack_composite_weight(__nv_bfloat16* dst, const float* src, int Cout, int Cin, float scale, const float* fir,
+                                 cudaStream_t st) {
+  const int64_t total = (int64_t)36 * Cout * Cin;
+  const int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)kNumSMs * 8);
+  pack_composite_weight_kernel<<<blocks, 256, 0, st>>>(dst, src, Cout, Cin, scale, fir[0], fir[1], fir[2], fir[3]);
+  return check_launch("pack_composite_weight");
+}
+
 __global__ void scale_copy_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n, float scale) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     dst[i] = src[i] * scale;

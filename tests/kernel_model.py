@@ -33,6 +33,46 @@ def _tap_conv(x, w, taps, oh, ow):
     return out
 
 
+def composite_weights(wt, f):
+    """Mirrors pack_composite_weight_kernel (pointwise.cu): wt [Cout,Cin,3,3] (already scaled), f = flipped blur taps * 2 / sum.
+    Returns Wc [4 phases][3 dy][3 dx][Cout][Cin]: transposed conv (stride 2) + blur as a 3x3 conv per output phase."""
+    cout, cin = wt.shape[:2]
+    wc = wt.new_zeros(4, 3, 3, cout, cin)
+    for ph in range(4):
+        py, px = ph >> 1, ph & 1
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                for i in range(4):
+                    kh = py + i - 1 - 2 * dy
+                    if kh < 0 or kh > 2:
+                        continue
+                    for j in range(4):
+                        kw = px + j - 1 - 2 * dx
+                        if kw < 0 or kw > 2:
+                            continue
+                        wc[ph, dy + 1, dx + 1] += f[i] * f[j] * wt[:, :, kh, kw]
+    return wc
+
+
+def _composite_upconv(x, wc, H):
+    """x: [B,H,H,Cin] -> blur(convT(x)) [B,2H,2H,Cout] via the per-phase 3x3 convs at input resolution."""
+    b = x.shape[0]
+    cout = wc.shape[3]
+    out = x.new_zeros(b, 2 * H, 2 * H, cout)
+    for ph in range(4):
+        py, px = ph >> 1, ph & 1
+        acc = x.new_zeros(b, H, H, cout)
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                shifted = x.new_zeros(x.shape)
+                y0, y1 = max(0, -dy), min(H, H - dy)
+                x0, x1 = max(0, -dx), min(H, H - dx)
+                shifted[:, y0:y1, x0:x1] = x[:, y0 + dy:y1 + dy, x0 + dx:x1 + dx]
+                acc = acc + torch.einsum("bhwc,oc->bhwo", shifted, wc[ph, dy + 1, dx + 1])
+        out[:, py::2, px::2] = acc
+    return out
+
+
 def _upsample2x(skip, f):
     """skip: [B,3,h,w] -> [B,3,2h,2w]; mirrors upsample2x_at (conv_common.cuh)."""
     b, c, h, w = skip.shape
@@ -51,7 +91,7 @@ def _upsample2x(skip, f):
     return out
 
 
-def fused_forward_model(sd, latent, noise, spec, dtype=torch.float64):
+def fused_forward_model(sd, latent, noise, spec, dtype=torch.float64, composite=False):
     """Returns (image, {name: unscaled activation NCHW}, {k: skip})."""
     sd = {k: v.to(dtype) for k, v in sd.items()}
     latent = latent.to(dtype)
@@ -87,6 +127,13 @@ def fused_forward_model(sd, latent, noise, spec, dtype=torch.float64):
         nz = noise[ni].to(dtype)
         nw, bias = sd[name + ".noise.weight"], sd[name + ".activate.bias"]
         H = x.shape[1]
+        if up and composite:
+            v = _composite_upconv(x, composite_weights(wt, f), H) * d[:, None, None, :]
+            v = v + nw * nz.permute(0, 2, 3, 1) + bias
+            y = torch.where(v > 0, v, 0.2 * v) * math.sqrt(2)
+            acts[name] = y.permute(0, 3, 1, 2)
+            x = y * s[nxt][:, None, None, :]
+            continue
         if up:
             t = x.new_zeros(B, 2 * H + 2, 2 * H + 2, cout)
             for ph in range(4):

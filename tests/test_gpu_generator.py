@@ -221,3 +221,42 @@ def test_bf16_latent_gradient_direction():
         grads[dt] = lc.grad.flatten().double()
     cos = torch.nn.functional.cosine_similarity(grads[torch.float32], grads[torch.bfloat16], dim=0).item()
     assert cos >= 0.995, cos
+
+
+@pytest.mark.parametrize("size,batch", [(32, 2), (64, 3), (128, 1)])
+def test_composite_upconv_matches_oracle(size, batch, monkeypatch):
+    """Transposed conv + blur folded into one tcgen05 conv (composite 6x6 kernel, N = 4 phases x Cout),
+    forced on for every up layer >= 16 px; bf16 gate vs the float64 oracle and vs the two-kernel path."""
+    from latent2im_b200.graphs.stylegan_v2_real.networks import Generator
+    spec = GeneratorSpec(size=size, style_dim=64, n_mlp=1)
+    lat = _latent(spec, batch)
+    noise = synthetic_noise(spec.num_layers, batch)
+    imgs = {}
+    for res in ("16", "4096"):
+        monkeypatch.setenv("L2I_COMPOSITE_RES", res)
+        gen = load_synthetic(Generator(size, 64, 1), seed=0)
+        sd = {k: v.double() for k, v in gen.state_dict().items()}
+        gen = gen.cuda()
+        gen.set_native(dtype=torch.bfloat16)
+        imgs[res], _ = gen(lat.cuda(), input_is_latent=True, noise=[n.cuda() for n in noise])
+    ref = generator_forward_ref(sd, lat.double(), noise, spec)
+    assert _psnr(imgs["16"].cpu().double(), ref) >= 45.0
+    assert _psnr(imgs["16"].double(), imgs["4096"].double()) >= 46.0
+
+
+@pytest.mark.parametrize("size,batch", [(256, 2), (1024, 1)])
+def test_full_size_bf16_vs_fp32_kernels(size, batch):
+    """BASELINE.json sizes: the bf16 tcgen05 path (composite up-convs, halo-resident and pair-packed
+    layers) against the fp32 CUDA-core path, which is itself gated against the oracle and the
+    reference's goldens at the sizes the oracle finishes in seconds.  PSNR >= 45 dB (peak-to-peak 2)."""
+    from latent2im_b200.graphs.stylegan_v2_real.networks import Generator
+    gen = load_synthetic(Generator(size, 512, 8), seed=0).cuda()
+    z = torch.tensor(synthetic_z(batch, 0), dtype=torch.float32).cuda()
+    lat = gen.style(z)[:, None, :].repeat(1, gen.n_latent, 1)
+    noise = [n.cuda() for n in synthetic_noise(gen.num_layers, batch)]
+    out = {}
+    for dt in (torch.float32, torch.bfloat16):
+        gen.set_native(dtype=dt)
+        out[dt], _ = gen(lat, input_is_latent=True, noise=noise)
+    assert torch.isfinite(out[torch.bfloat16]).all()
+    assert _psnr(out[torch.bfloat16].double(), out[torch.float32].double()) >= 45.0
