@@ -13,7 +13,7 @@
 //                                           next-style scale/ToRGB/skip -> global stores
 // Pipelines: smem ring (full/empty mbarriers, TMA <-> MMA) and a 2-deep TMEM accumulator ring
 // (tmem_full/tmem_empty, MMA <-> epilogue) so the epilogue of tile i overlaps the MMAs of tile i+1.
-#include "tc_ptx.cuh"
+#include "tc_epilogue.cuh"
 
 namespace l2i {
 
@@ -44,10 +44,8 @@ struct SmemLayout {
   static constexpr int kABytes = kBlockM * BLOCK_K * 2;
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kEpiFloats = 6 * BLOCK_N;                      // per group: dS, bS, sn, w0, w1, w2
-  static constexpr int kEpiBytes = GROUPS * kEpiFloats * 4;
-  static constexpr int kBarrierBytes = 256;
-  static constexpr int kTotal = STAGES * kStageBytes + kEpiBytes + kBarrierBytes + 1024;  // + alignment slack
+  static constexpr int kEpiFloats = 6 * BLOCK_N;                      // per group: dS, bS, sn, w0, w1, w2 (static smem)
+  static constexpr int kTotal = STAGES * kStageBytes + 1024;          // dynamic smem: the operand ring + alignment slack
   static constexpr int kThreads = 128 + GROUPS * 128;
 };
 
@@ -55,7 +53,7 @@ __device__ __forceinline__ void group_sync(int group) {
   asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
 }
 
-template <int BLOCK_N, int BLOCK_K, int STAGES, int GROUPS>
+template <int BLOCK_N, int BLOCK_K, int STAGES, int GROUPS, int EPI>
 __global__ void __launch_bounds__(128 + GROUPS * 128, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ TcParams p) {
@@ -68,13 +66,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns must be a power of two <= 512");
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  float* epi_smem = (float*)(smem + STAGES * L::kStageBytes);
-  uint64_t* full_bar = (uint64_t*)(smem + STAGES * L::kStageBytes + L::kEpiBytes);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;
-  uint64_t* tmem_empty = tmem_full + GROUPS;
-  uint32_t* tmem_base_smem = (uint32_t*)(tmem_empty + GROUPS);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned operand ring
+  __shared__ __align__(16) float epi_smem[GROUPS * L::kEpiFloats];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tmem_full[GROUPS];
+  __shared__ __align__(8) uint64_t tmem_empty[GROUPS];
+  __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -93,11 +91,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_base_smem, kTmemCols);
+  if (warp == 2) tmem_alloc(&tmem_base_smem, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_smem;
+  const uint32_t tmem_base = tmem_base_smem;
 
   const int kchunks = p.Cin / BLOCK_K;
   const int tiles_m = p.tiles_x * p.tiles_y * p.B;
@@ -182,10 +180,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     float* s_n = sp + 2 * BLOCK_N;   // next-layer style
     float* s_w = sp + 3 * BLOCK_N;   // ToRGB weights, 3 x BLOCK_N
     constexpr float kSqrt2 = 1.4142135623730951f;
-    const float nw = (e.noise != nullptr && e.noise_w != nullptr) ? __ldg(e.noise_w) * kSqrt2 : 0.f;
+    const float nw = (EPI != EPI_RAW && e.noise != nullptr && e.noise_w != nullptr) ? __ldg(e.noise_w) * kSqrt2 : 0.f;
     const int64_t plane = (int64_t)p.out_H * p.out_W;
     const int lx = row % p.bw, ly = row / p.bw;
-    const bool comp = p.up_cout > 0;
+    const bool comp = EPI == EPI_ACT && p.up_cout > 0;
+    const bool raw_fp16 = e.raw_fp16 != 0;
     uint32_t acc_phase = 0;
     int staged_key = -1;
     int it = 0;
@@ -206,13 +205,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int j = gtid; j < BLOCK_N; j += 128) {
           const int co = comp ? (co0 + j) % p.up_cout : co0 + j;
           const float d = e.demod != nullptr ? __ldg(e.demod + (int64_t)b * e.demod_bs + co) : 1.f;
-          if (e.mode == 0) {
+          if (EPI != EPI_RAW) {
             s_d[j] = d * kSqrt2;
             s_b[j] = __ldg(e.bias + co) * kSqrt2;
             s_n[j] = e.s_next ? __ldg(e.s_next + (int64_t)b * e.s_next_bs + co) : 1.f;
+            if (EPI == EPI_ACT_RGB) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
-              s_w[c * BLOCK_N + j] = e.wr ? __ldg(e.wr + (int64_t)b * e.wr_bs + c * p.Cout + co) : 0.f;
+              for (int c = 0; c < 3; ++c)
+                s_w[c * BLOCK_N + j] = e.wr ? __ldg(e.wr + (int64_t)b * e.wr_bs + c * p.Cout + co) : 0.f;
+            }
           } else {
             s_d[j] = d;
           }
@@ -223,13 +224,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
       // ---- issue every global load of this tile before waiting for the accumulator ----
       float nz = 0.f, nz1 = 0.f, nz2 = 0.f, nz3 = 0.f;
-      if (e.mode == 0 && e.noise != nullptr && valid) {
+      if (EPI != EPI_RAW && e.noise != nullptr && valid) {
         const float* np = e.noise + (int64_t)b * e.noise_bs + (int64_t)Y * p.out_W + X;
-        nz = nw * __ldg(np);
-        if (comp) { nz1 = nw * __ldg(np + 1); nz2 = nw * __ldg(np + p.out_W); nz3 = nw * __ldg(np + p.out_W + 1); }
+        if (comp) {
+          const float2 n01 = __ldg(reinterpret_cast<const float2*>(np));
+          const float2 n23 = __ldg(reinterpret_cast<const float2*>(np + p.out_W));
+          nz = nw * n01.x; nz1 = nw * n01.y; nz2 = nw * n23.x; nz3 = nw * n23.y;
+        } else {
+          nz = nw * __ldg(np);
+        }
       }
       float up[3] = {0.f, 0.f, 0.f};
-      if (e.mode == 0 && e.fused_skip && valid) {
+      if (EPI == EPI_ACT_RGB && e.fused_skip && valid) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           up[c] = __ldg(e.rgb_bias + c);
@@ -238,10 +244,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       }
       __nv_bfloat16* outp = nullptr;
-      if (!comp && valid && e.out != nullptr && (e.mode == 1 || e.s_next != nullptr))
+      if (!comp && valid && e.out != nullptr && (EPI == EPI_RAW || e.s_next != nullptr))
         outp = (__nv_bfloat16*)e.out + (((int64_t)b * p.out_H + Y) * p.out_W + X) * p.Cout + nt * BLOCK_N;
       __nv_bfloat16* yp = nullptr;
-      if (!comp && valid && e.mode == 0 && e.y_out != nullptr)
+      if (!comp && valid && EPI != EPI_RAW && e.y_out != nullptr)
         yp = (__nv_bfloat16*)e.y_out + (((int64_t)b * p.out_H + Y) * p.out_W + X) * p.Cout + nt * BLOCK_N;
       float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
 
@@ -268,68 +274,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
         tmem_ld_wait();
-        uint32_t packed[16];
-        uint32_t ypacked[16];
-#pragma unroll
-        for (int j4 = 0; j4 < 32; j4 += 4) {
-          const float4 d4 = *reinterpret_cast<const float4*>(s_d + c0 + j4);
-          float o[4];
-          float yy[4] = {0.f, 0.f, 0.f, 0.f};
-          if (e.mode == 0) {
-            const float4 b4 = *reinterpret_cast<const float4*>(s_b + c0 + j4);
-            const float4 n4 = *reinterpret_cast<const float4*>(s_n + c0 + j4);
-            const float4 w0 = *reinterpret_cast<const float4*>(s_w + c0 + j4);
-            const float4 w1 = *reinterpret_cast<const float4*>(s_w + BLOCK_N + c0 + j4);
-            const float4 w2 = *reinterpret_cast<const float4*>(s_w + 2 * BLOCK_N + c0 + j4);
-            const float dd[4] = {d4.x, d4.y, d4.z, d4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
-            const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
-            const float a0[4] = {w0.x, w0.y, w0.z, w0.w}, a1[4] = {w1.x, w1.y, w1.z, w1.w}, a2[4] = {w2.x, w2.y, w2.z, w2.w};
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-              float x = fmaf(__uint_as_float(v[j4 + h]), dd[h], bb[h] + nzc);
-              x = fmaxf(x, 0.2f * x);  // leaky relu (the sqrt(2) gain is folded into dd / bb / nz)
-              rgb0 = fmaf(a0[h], x, rgb0);
-              rgb1 = fmaf(a1[h], x, rgb1);
-              rgb2 = fmaf(a2[h], x, rgb2);
-              yy[h] = x;
-              o[h] = x * nn[h];
-            }
-          } else {
-            o[0] = __uint_as_float(v[j4]) * d4.x; o[1] = __uint_as_float(v[j4 + 1]) * d4.y;
-            o[2] = __uint_as_float(v[j4 + 2]) * d4.z; o[3] = __uint_as_float(v[j4 + 3]) * d4.w;
-          }
-          {
-            __nv_bfloat162 y0 = __floats2bfloat162_rn(yy[0], yy[1]), y1 = __floats2bfloat162_rn(yy[2], yy[3]);
-            ypacked[j4 >> 1] = *reinterpret_cast<uint32_t*>(&y0);
-            ypacked[(j4 >> 1) + 1] = *reinterpret_cast<uint32_t*>(&y1);
-          }
-          if (e.mode == 1 && e.raw_fp16) {
-            __half2 p0 = __floats2half2_rn(o[0], o[1]), p1 = __floats2half2_rn(o[2], o[3]);
-            packed[j4 >> 1] = *reinterpret_cast<uint32_t*>(&p0);
-            packed[(j4 >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p1);
-          } else {
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
-            packed[j4 >> 1] = *reinterpret_cast<uint32_t*>(&p0);
-            packed[(j4 >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p1);
-          }
-        }
-        if (yc != nullptr) {
-          uint4* dst = reinterpret_cast<uint4*>(yc);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) dst[k] = make_uint4(ypacked[4 * k], ypacked[4 * k + 1], ypacked[4 * k + 2], ypacked[4 * k + 3]);
-        }
-        if (outc != nullptr) {
-          uint4* dst = reinterpret_cast<uint4*>(outc);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) dst[k] = make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
-        }
+        epilogue_chunk32<EPI>(v, s_d + c0, s_b + c0, s_n + c0, s_w + c0, s_w + BLOCK_N + c0, s_w + 2 * BLOCK_N + c0, nzc,
+                              raw_fp16, rgb0, rgb1, rgb2, outc, yc);
       }
       // all TMEM reads of this accumulator stage are complete (wait::ld above): hand it back
       tc_fence_before();
       mbar_arrive(&tmem_empty[group]);
       acc_phase ^= 1;
 
-      if (e.mode == 0 && e.wr != nullptr && valid) {
+      if (EPI == EPI_ACT_RGB && e.wr != nullptr && valid) {
         const float r3[3] = {rgb0, rgb1, rgb2};
         if (e.fused_skip) {
 #pragma unroll
@@ -401,8 +354,8 @@ bool tmap_available() { return get_encode_fn() != nullptr; }
 
 namespace {
 
-template <int BLOCK_N, int BLOCK_K, int STAGES, int GROUPS>
-int launch_variant(const void* in, const __nv_bfloat16* w, TcParams& p, cudaStream_t st) {
+template <int BLOCK_N, int BLOCK_K, int STAGES, int GROUPS, int EPI>
+int launch_variant_epi(const void* in, const __nv_bfloat16* w, TcParams& p, cudaStream_t st) {
   using L = SmemLayout<BLOCK_N, BLOCK_K, STAGES, GROUPS>;
   p.a_bytes = (uint32_t)(p.bw * p.bh * BLOCK_K * 2);
   static_assert(L::kTotal <= 227 * 1024, "shared memory budget");
@@ -420,7 +373,7 @@ int launch_variant(const void* in, const __nv_bfloat16* w, TcParams& p, cudaStre
     const uint32_t box[3] = {(uint32_t)BLOCK_K, (uint32_t)BLOCK_N, 1};
     L2I_TRY(make_tmap(&tb, w, 3, dims, str, box, swz));
   }
-  auto kern = conv_tc_kernel<BLOCK_N, BLOCK_K, STAGES, GROUPS>;
+  auto kern = conv_tc_kernel<BLOCK_N, BLOCK_K, STAGES, GROUPS, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     L2I_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -429,6 +382,13 @@ int launch_variant(const void* in, const __nv_bfloat16* w, TcParams& p, cudaStre
   const int grid = std::min(p.total_tiles, kNumSMs);
   kern<<<grid, L::kThreads, L::kTotal, st>>>(ta, tb, p);
   return check_launch("conv_tc");
+}
+
+template <int BLOCK_N, int BLOCK_K, int STAGES, int GROUPS>
+int launch_variant(const void* in, const __nv_bfloat16* w, TcParams& p, cudaStream_t st) {
+  if (p.e.mode == 1) return launch_variant_epi<BLOCK_N, BLOCK_K, STAGES, GROUPS, EPI_RAW>(in, w, p, st);
+  if (p.e.wr != nullptr) return launch_variant_epi<BLOCK_N, BLOCK_K, STAGES, GROUPS, EPI_ACT_RGB>(in, w, p, st);
+  return launch_variant_epi<BLOCK_N, BLOCK_K, STAGES, GROUPS, EPI_ACT>(in, w, p, st);
 }
 
 int pick_block_n(int cout) { return cout >= 256 ? 256 : cout; }

@@ -16,7 +16,7 @@
 // Output tile = 8 units wide x 16 units tall = 128 UMMA rows; an 8-row UMMA group is one image row
 // of the tile and the halo tile pitch is 16 units (2048 B), so the descriptor's stride-byte-offset is
 // a whole number of 1024-byte swizzle atoms and only the start address (tap shift) moves.
-#include "tc_ptx.cuh"
+#include "tc_epilogue.cuh"
 
 namespace l2i {
 
@@ -76,8 +76,8 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, u
 }
 
 // N = GEMM N (Cout, or 4 * Cout for the composite up-conv), STAGES = A halo stages, PAIR = Cin 32 pair-packed
-// units, COMP = composite up-conv (N = 4 phases x 32 channels, fused blur: SURVEY 0.6b)
-template <int N, int STAGES, int NACC, bool PAIR, bool COMP>
+// units, COMP = composite up-conv (N = 4 phases x 32 channels, fused blur: SURVEY 0.6b), EPI = fused epilogue kind
+template <int N, int STAGES, int NACC, bool PAIR, bool COMP, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ HaloParams p) {
@@ -86,19 +86,19 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM budget");
   constexpr int CO = COMP ? N / 4 : N;   // distinct output channels whose epilogue vectors are staged
   constexpr int kEpiFloats = 6 * CO;
-  static_assert(!COMP || (CO == 32 && NACC == 1), "composite variant: 4 phases x 32 channels in one accumulator");
+  static_assert(!COMP || (CO == 32 && NACC == 1 && EPI == EPI_ACT), "composite variant: 4 phases x 32 channels in one accumulator");
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // A halo stages, then the resident weights
   uint8_t* smem_w = smem + STAGES * kHaloBytes;
   const int wbytes = p.nwtiles * kWTileBytes;
-  float* epi_smem = (float*)(smem_w + ((wbytes + 1023) & ~1023));
-  uint64_t* full_bar = (uint64_t*)(epi_smem + kGroups * kEpiFloats);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;
-  uint64_t* tmem_empty = tmem_full + kGroups;
-  uint64_t* w_bar = tmem_empty + kGroups;
-  uint32_t* tmem_base_smem = (uint32_t*)(w_bar + 1);
+  __shared__ __align__(16) float epi_smem[kGroups * kEpiFloats];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tmem_full[kGroups];
+  __shared__ __align__(8) uint64_t tmem_empty[kGroups];
+  __shared__ __align__(8) uint64_t w_bar;
+  __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -108,14 +108,14 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < kGroups; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
-    mbar_init(w_bar, 1);
+    mbar_init(&w_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_base_smem, kTmemCols);
+  if (warp == 2) tmem_alloc(&tmem_base_smem, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_smem;
+  const uint32_t tmem_base = tmem_base_smem;
 
   auto decode = [&](int tile, int& x0, int& y0, int& b) {
     const int tx = tile % p.tiles_x;
@@ -128,8 +128,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0) {
     // ===================== TMA producer: weights once, then one halo tile per output tile ==========
     if (lane == 0) {
-      mbar_expect_tx(w_bar, (uint32_t)wbytes);
-      for (int t = 0; t < p.nwtiles; ++t) tma_load_3d(smem_w + t * kWTileBytes, &tmap_w, w_bar, 0, 0, t);
+      mbar_expect_tx(&w_bar, (uint32_t)wbytes);
+      for (int t = 0; t < p.nwtiles; ++t) tma_load_3d(smem_w + t * kWTileBytes, &tmap_w, &w_bar, 0, 0, t);
       int stage = 0;
       uint32_t phase_bit = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -144,7 +144,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      mbar_wait(w_bar, 0);
+      mbar_wait(&w_bar, 0);
       tc_fence_after();
       const uint32_t w_base = smem_u32(smem_w);
       int stage = 0;
@@ -190,9 +190,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     float* s_n = sp + 2 * CO;
     float* s_w = sp + 3 * CO;
     constexpr float kSqrt2 = 1.4142135623730951f;
-    const float nw = (e.noise != nullptr && e.noise_w != nullptr) ? __ldg(e.noise_w) * kSqrt2 : 0.f;
+    const float nw = (EPI != EPI_RAW && e.noise != nullptr && e.noise_w != nullptr) ? __ldg(e.noise_w) * kSqrt2 : 0.f;
     const int64_t plane = (int64_t)p.out_H * p.out_W;
     const int lx = row & 7, ly = row >> 3;
+    const bool raw_fp16 = e.raw_fp16 != 0;
     uint32_t grp_phase = 0;
     int staged_b = -1;
     int it = 0;
@@ -207,12 +208,14 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         halo_group_sync(group);
         for (int j = gtid; j < CO; j += 128) {
           const float d = e.demod != nullptr ? __ldg(e.demod + (int64_t)b * e.demod_bs + j) : 1.f;
-          if (e.mode == 0) {
+          if (EPI != EPI_RAW) {
             s_d[j] = d * kSqrt2;
             s_b[j] = __ldg(e.bias + j) * kSqrt2;
             s_n[j] = e.s_next ? __ldg(e.s_next + (int64_t)b * e.s_next_bs + j) : 1.f;
+            if (EPI == EPI_ACT_RGB) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) s_w[c * CO + j] = e.wr ? __ldg(e.wr + (int64_t)b * e.wr_bs + c * p.Cout + j) : 0.f;
+              for (int c = 0; c < 3; ++c) s_w[c * CO + j] = e.wr ? __ldg(e.wr + (int64_t)b * e.wr_bs + c * p.Cout + j) : 0.f;
+            }
           } else {
             s_d[j] = d;
           }
@@ -241,9 +244,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         ok[a] = in_grid && Ys[a] < p.out_H && Xs[a] < p.out_W;
         nz[a] = 0.f;
         up[a][0] = up[a][1] = up[a][2] = 0.f;
-        if (!COMP && e.mode == 0 && ok[a]) {
+        if (!COMP && EPI != EPI_RAW && ok[a]) {
           if (e.noise != nullptr) nz[a] = nw * __ldg(e.noise + (int64_t)b * e.noise_bs + (int64_t)Ys[a] * p.out_W + Xs[a]);
-          if (e.fused_skip) {
+          if (EPI == EPI_ACT_RGB && e.fused_skip) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
               up[a][c] = __ldg(e.rgb_bias + c);
@@ -261,9 +264,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((group * NACC + a) * N);
         const int64_t pix = ((int64_t)b * p.out_H + Ys[a]) * p.out_W + Xs[a];
         __nv_bfloat16* outp = nullptr;
-        if (!COMP && ok[a] && e.out != nullptr && (e.mode == 1 || e.s_next != nullptr)) outp = (__nv_bfloat16*)e.out + pix * p.Cout;
+        if (!COMP && ok[a] && e.out != nullptr && (EPI == EPI_RAW || e.s_next != nullptr)) outp = (__nv_bfloat16*)e.out + pix * p.Cout;
         __nv_bfloat16* yp = nullptr;
-        if (!COMP && ok[a] && e.mode == 0 && e.y_out != nullptr) yp = (__nv_bfloat16*)e.y_out + pix * p.Cout;
+        if (!COMP && ok[a] && EPI != EPI_RAW && e.y_out != nullptr) yp = (__nv_bfloat16*)e.y_out + pix * p.Cout;
         float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
 #pragma unroll 1
         for (int c0 = 0; c0 < N; c0 += 32) {
@@ -276,7 +279,6 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (COMP) {                          // chunk = output phase
             const int phc = c0 >> 5;
             nzc = phc == 0 ? nzq[0] : (phc == 1 ? nzq[1] : (phc == 2 ? nzq[2] : nzq[3]));
-            outc = yc = nullptr;
             if (ok[a]) {
               const int Xc = Xs[a] + (phc & 1);
               const int64_t pixc = ((int64_t)b * p.out_H + Ys[a] + (phc >> 1)) * p.out_W + Xc;
@@ -286,60 +288,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
           }
           tmem_ld_wait();
-          uint32_t packed[16], ypacked[16];
-#pragma unroll
-          for (int j4 = 0; j4 < 32; j4 += 4) {
-            const float4 d4 = *reinterpret_cast<const float4*>(s_d + cs + j4);
-            float o[4], yy[4] = {0.f, 0.f, 0.f, 0.f};
-            if (e.mode == 0) {
-              const float4 b4 = *reinterpret_cast<const float4*>(s_b + cs + j4);
-              const float4 n4 = *reinterpret_cast<const float4*>(s_n + cs + j4);
-              const float4 w0 = *reinterpret_cast<const float4*>(s_w + cs + j4);
-              const float4 w1 = *reinterpret_cast<const float4*>(s_w + CO + cs + j4);
-              const float4 w2 = *reinterpret_cast<const float4*>(s_w + 2 * CO + cs + j4);
-              const float dd[4] = {d4.x, d4.y, d4.z, d4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w}, nn[4] = {n4.x, n4.y, n4.z, n4.w};
-              const float a0[4] = {w0.x, w0.y, w0.z, w0.w}, a1[4] = {w1.x, w1.y, w1.z, w1.w}, a2[4] = {w2.x, w2.y, w2.z, w2.w};
-#pragma unroll
-              for (int h = 0; h < 4; ++h) {
-                float x = fmaf(__uint_as_float(v[j4 + h]), dd[h], bb[h] + nzc);
-                x = fmaxf(x, 0.2f * x);
-                rgb0 = fmaf(a0[h], x, rgb0);
-                rgb1 = fmaf(a1[h], x, rgb1);
-                rgb2 = fmaf(a2[h], x, rgb2);
-                yy[h] = x;
-                o[h] = x * nn[h];
-              }
-            } else {
-              o[0] = __uint_as_float(v[j4]) * d4.x; o[1] = __uint_as_float(v[j4 + 1]) * d4.y;
-              o[2] = __uint_as_float(v[j4 + 2]) * d4.z; o[3] = __uint_as_float(v[j4 + 3]) * d4.w;
-            }
-            {
-              __nv_bfloat162 y0 = __floats2bfloat162_rn(yy[0], yy[1]), y1 = __floats2bfloat162_rn(yy[2], yy[3]);
-              ypacked[j4 >> 1] = *reinterpret_cast<uint32_t*>(&y0);
-              ypacked[(j4 >> 1) + 1] = *reinterpret_cast<uint32_t*>(&y1);
-            }
-            if (e.mode == 1 && e.raw_fp16) {
-              __half2 p0 = __floats2half2_rn(o[0], o[1]), p1 = __floats2half2_rn(o[2], o[3]);
-              packed[j4 >> 1] = *reinterpret_cast<uint32_t*>(&p0);
-              packed[(j4 >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p1);
-            } else {
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
-              packed[j4 >> 1] = *reinterpret_cast<uint32_t*>(&p0);
-              packed[(j4 >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p1);
-            }
-          }
-          if (yc != nullptr) {
-            uint4* dst = reinterpret_cast<uint4*>(yc);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) dst[k] = make_uint4(ypacked[4 * k], ypacked[4 * k + 1], ypacked[4 * k + 2], ypacked[4 * k + 3]);
-          }
-          if (outc != nullptr) {
-            uint4* dst = reinterpret_cast<uint4*>(outc);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) dst[k] = make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
-          }
+          epilogue_chunk32<EPI>(v, s_d + cs, s_b + cs, s_n + cs, s_w + cs, s_w + CO + cs, s_w + 2 * CO + cs, nzc, raw_fp16,
+                                rgb0, rgb1, rgb2, outc, yc);
         }
-        if (e.mode == 0 && e.wr != nullptr && ok[a]) {
+        if (EPI == EPI_ACT_RGB && e.wr != nullptr && ok[a]) {
           const float r3[3] = {rgb0, rgb1, rgb2};
           if (e.fused_skip) {
 #pragma unroll
@@ -364,15 +316,15 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
-template <int N, int STAGES, int NACC, bool PAIR, bool COMP = false>
+template <int N, int STAGES, int NACC, bool PAIR, bool COMP, int EPI>
 int launch_halo_variant(const CUtensorMap& ta, const CUtensorMap& tw, const HaloParams& p, cudaStream_t st) {
-  const int wbytes = ((p.nwtiles * N * 128) + 1023) & ~1023;
-  const int smem = STAGES * kHaloBytes + wbytes + kGroups * 6 * (COMP ? N / 4 : N) * 4 + 256 + 1024;
+  const int wbytes = p.nwtiles * N * 128;
+  const int smem = STAGES * kHaloBytes + wbytes + 1024;   // + alignment slack; epilogue vectors and barriers are static
   if (smem > 227 * 1024) {
     set_error("conv_tc_halo: shared memory budget exceeded (%d bytes)", smem);
     return L2I_ERR_UNSUPPORTED;
   }
-  auto kern = conv_tc_halo_kernel<N, STAGES, NACC, PAIR, COMP>;
+  auto kern = conv_tc_halo_kernel<N, STAGES, NACC, PAIR, COMP, EPI>;
   static int attr_smem = 0;
   if (attr_smem < smem) {
     L2I_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -404,6 +356,8 @@ bool conv_tc_halo_supported(const ConvGeom& g, const EpiParams& e) {
   if (g.up_cout > 0)   // composite up-conv 64 -> 32: GEMM N = 128, weights (9 x 16 KB) resident
     return g.nphase == 1 && g.Cin == 64 && g.up_cout == 32 && g.Cout == 128 && e.mode == 0 && e.wr == nullptr && (g_halo_mask & 8) != 0;
   if (!(g.Cout == 32 || g.Cout == 64)) return false;
+  if (g.nphase == 1 && (e.mode != 0 || e.wr == nullptr)) return false;   // plain variants are compiled with the act + ToRGB epilogue
+  if (g.nphase == 4 && e.mode != 1) return false;                        // transposed-conv variant writes the raw t tensor
   if (g.nphase == 1 && g.Cin == 64) return (g_halo_mask & 1) != 0;
   if (g.nphase == 4 && g.Cin == 64 && g.Cout == 32) return (g_halo_mask & 2) != 0;   // 4 accumulators x 32 columns x 4 groups = 512 TMEM columns
   if (g.nphase == 1 && g.Cin == 32 && g.Cout == 32 && (g.H % 2 == 0)) return (g_halo_mask & 4) != 0;  // caller provides pair-packed input
@@ -460,11 +414,11 @@ int launch_conv_tc_halo(const void* in, const __nv_bfloat16* w, const ConvGeom& 
   const int64_t total = (int64_t)p.tiles_x * p.tiles_y * g.B;
   if (total <= 0 || total > 0x7fffffff) { set_error("conv_tc_halo: bad tile count"); return L2I_ERR_INVALID_ARG; }
   p.total_tiles = (int)total;
-  if (g.up_cout > 0) return launch_halo_variant<128, 2, 1, false, true>(ta, tw, p, st);
-  if (g.nphase == 4) return launch_halo_variant<32, 4, 4, false>(ta, tw, p, st);
-  if (pair) return launch_halo_variant<32, 4, 2, true>(ta, tw, p, st);
-  if (g.Cout == 64) return launch_halo_variant<64, 3, 1, false>(ta, tw, p, st);
-  return launch_halo_variant<32, 4, 1, false>(ta, tw, p, st);
+  if (g.up_cout > 0) return launch_halo_variant<128, 2, 1, false, true, EPI_ACT>(ta, tw, p, st);
+  if (g.nphase == 4) return launch_halo_variant<32, 4, 4, false, false, EPI_RAW>(ta, tw, p, st);
+  if (pair) return launch_halo_variant<32, 4, 2, true, false, EPI_ACT_RGB>(ta, tw, p, st);
+  if (g.Cout == 64) return launch_halo_variant<64, 3, 1, false, false, EPI_ACT_RGB>(ta, tw, p, st);
+  return launch_halo_variant<32, 4, 1, false, false, EPI_ACT_RGB>(ta, tw, p, st);
 }
 
 // Pair-packed weight tiles for Cin = 32: dst [12][Cout][64] bf16, tile (parity*2 + r)*3 + kw holds

@@ -63,14 +63,28 @@ TapList upconv_taps(int py, int px) {
   return t;
 }
 
-// Plain Cin == 32 layers run on the halo kernel with vertically pair-packed input units; their producer
-// (the blur of the preceding up-conv) then writes that layout directly.
-bool layer_uses_pair_halo(l2i_generator* g, const StyledConvLayer& L, int B) {
-  if (g->dtype != L2I_BF16 || g->conv_impl == 1 || L.up || L.split || L.cin != 32 || L.w_pair == nullptr) return false;
+// Plain 32 -> 32 layers on even images run on the 2x2-block kernel (plain NHWC input).
+bool layer_uses_quad(l2i_generator* g, const StyledConvLayer& L, int B) {
+  if (g->dtype != L2I_BF16 || g->conv_impl == 1 || L.up || L.split || L.w_quad == nullptr) return false;
   ConvGeom geom{};
   geom.B = B; geom.H = geom.W = L.res_in; geom.Cin = L.cin; geom.Cout = L.cout; geom.in_scale = 1; geom.weight_taps = 9;
   geom.OH = geom.OW = L.res_in; geom.nphase = 1; geom.out_scale = 1; geom.out_H = geom.out_W = L.res_out;
   EpiParams e{};
+  e.wr = g->wr_all;
+  e.fused_skip = 1;
+  return conv_tc_quad_supported(geom, e);
+}
+
+// Otherwise plain Cin == 32 layers run on the halo kernel with vertically pair-packed input units; their producer
+// (the blur of the preceding up-conv) then writes that layout directly.
+bool layer_uses_pair_halo(l2i_generator* g, const StyledConvLayer& L, int B) {
+  if (g->dtype != L2I_BF16 || g->conv_impl == 1 || L.up || L.split || L.cin != 32 || L.w_pair == nullptr) return false;
+  if (layer_uses_quad(g, L, B)) return false;
+  ConvGeom geom{};
+  geom.B = B; geom.H = geom.W = L.res_in; geom.Cin = L.cin; geom.Cout = L.cout; geom.in_scale = 1; geom.weight_taps = 9;
+  geom.OH = geom.OW = L.res_in; geom.nphase = 1; geom.out_scale = 1; geom.out_H = geom.out_W = L.res_out;
+  EpiParams e{};
+  e.wr = g->wr_all;  // plain layers always carry their ToRGB / rgb-partial epilogue
   return conv_tc_halo_supported(geom, e);
 }
 
@@ -78,6 +92,8 @@ int run_conv(l2i_generator* g, const StyledConvLayer& L, const void* in, const C
              cudaStream_t st) {
   if (g->dtype == L2I_F32) return launch_conv_simt<float>(in, L.w_f32, geom, e, st);
   const bool want_tc = g->conv_impl != 1;
+  if (want_tc && !L.split && L.w_quad != nullptr && !geom.in_pair_packed && conv_tc_quad_supported(geom, e))
+    return launch_conv_tc_quad(in, L.w_quad, geom, e, st);
   if (want_tc && !L.split && conv_tc_halo_supported(geom, e) && (geom.Cin != 32 || (L.w_pair != nullptr && geom.in_pair_packed)))
     return launch_conv_tc_halo(in, geom.Cin == 32 ? L.w_pair : L.w_bf16, geom, e, st);
   if (want_tc && conv_tc_supported(geom, e)) {
@@ -233,6 +249,7 @@ extern "C" int l2i_generator_create(l2i_generator_t** out, int size, int style_d
     L.split = dtype == L2I_BF16 && L.res_out <= g->split_max_res;
     if (rc == L2I_OK && dtype == L2I_BF16) rc = dev_alloc(g, &L.w_bf16, (int64_t)(L.split ? 18 : 9) * L.cin * L.cout);
     if (rc == L2I_OK && dtype == L2I_BF16 && L.cin == 32 && !L.up) rc = dev_alloc(g, &L.w_pair, (int64_t)12 * L.cout * 64);
+    if (rc == L2I_OK && dtype == L2I_BF16 && L.cin == 32 && L.cout == 32 && !L.up) rc = dev_alloc(g, &L.w_quad, (int64_t)128 * 512);
     L.composite = dtype == L2I_BF16 && L.up && g->conv_impl != 1 && L.res_out >= g->composite_min_res && L.cout % 32 == 0 &&
                   L.cin % 64 == 0;
     if (rc == L2I_OK && L.composite) rc = dev_alloc(g, &L.w_comp, (int64_t)36 * L.cin * L.cout);
@@ -316,6 +333,7 @@ extern "C" int l2i_generator_finalize(l2i_generator_t* g, void* stream) {
     L2I_TRY(launch_pack_conv_weight(L.w_f32, L.w_bf16, g->wsq_all + L.wsq_off, P(g, L.name + ".conv.weight"), L.cout,
                                     L.cin, 9, scale, L.split ? 1 : 0, st));
     if (L.w_pair) L2I_TRY(launch_pack_pair_weight(L.w_pair, P(g, L.name + ".conv.weight"), L.cout, scale, st));
+    if (L.w_quad) L2I_TRY(launch_pack_quad_weight(L.w_quad, P(g, L.name + ".conv.weight"), scale, st));
     if (L.w_comp) L2I_TRY(launch_pack_composite_weight(L.w_comp, P(g, L.name + ".conv.weight"), L.cout, L.cin, scale, g->fir, st));
     L2I_TRY(launch_scale_copy(g->mod_w_all + (int64_t)L.s_off * D, P(g, L.name + ".conv.modulation.weight"),
                               (int64_t)L.cin * D, mod_scale, st));

@@ -16,6 +16,9 @@ int conv_tc_block_n(const ConvGeom& g);
 bool conv_tc_halo_supported(const ConvGeom& g, const EpiParams& e);
 int launch_conv_tc_halo(const void* in, const __nv_bfloat16* w, const ConvGeom& g, const EpiParams& e, cudaStream_t st);
 int launch_pack_pair_weight(__nv_bfloat16* dst, const float* src, int Cout, float scale, cudaStream_t st);
+bool conv_tc_quad_supported(const ConvGeom& g, const EpiParams& e);
+int launch_conv_tc_quad(const void* in, const __nv_bfloat16* w, const ConvGeom& g, const EpiParams& e, cudaStream_t st);
+int launch_pack_quad_weight(__nv_bfloat16* dst, const float* src, float scale, cudaStream_t st);
 int launch_pack_composite_weight(__nv_bfloat16* dst, const float* src, int Cout, int Cin, float scale, const float* fir, cudaStream_t st);
 template <typename T, typename TIN>
 int launch_blur_act(void*, void*, const void*, int, int, int, int, int, int, const float*, int64_t, const float*,
@@ -47,6 +50,7 @@ struct StyledConvLayer {
   float* w_f32 = nullptr;            // [9][Cin][Cout]
   __nv_bfloat16* w_bf16 = nullptr;   // [9][Cout][Cin], or [18][Cout][Cin] = bf16 hi halves then lo residuals (split)
   __nv_bfloat16* w_pair = nullptr;   // Cin == 32 plain layers: [12][Cout][64] pair-packed tiles for the halo kernel
+  __nv_bfloat16* w_quad = nullptr;   // 32 -> 32 plain layers: [8][128][64] 2x2-block weight matrix (conv_tc_quad.cu)
   __nv_bfloat16* w_comp = nullptr;   // composite up-conv (transposed conv + blur folded): [9][4*Cout][Cin], rows (phase, co)
   bool composite = false;            // inference forward of this up layer runs the composite kernel (no t intermediate)
   bool split = false;                // tensor-core path uses hi + lo weights (K doubled) to remove the weight rounding error
