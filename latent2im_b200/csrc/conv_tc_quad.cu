@@ -15,7 +15,10 @@
 // The 128 KB weight matrix stays resident in shared memory for the lifetime of the persistent CTA.
 //
 // Epilogue (per thread = one block = four pixels x 32 channels): demod, noise, bias, leaky-relu, ToRGB 1x1,
-// bias + 2x FIR up-sampling of the skip image (ToRGB.forward, networks.py:349-358), float2 stores.
+// bias + 2x FIR up-sampling of the skip image (ToRGB.forward, networks.py:349-358), float2 stores.  It walks the
+// accumulator in groups of 8 channels x 4 pixels so the per-channel vectors are fetched from shared memory once
+// per block, and the (8+2) x (16+2) low-resolution skip patch of the tile is TMA-loaded per accumulator stage
+// (out-of-image samples zero-filled = upfirdn2d's zero padding), so the epilogue issues no gather loads.
 #include "tc_epilogue.cuh"
 
 namespace l2i {
@@ -32,17 +35,21 @@ constexpr int kQRowPitch = kQHaloPairs * 128;             // 1280 bytes per halo
 constexpr int kQHaloBytes = kQHaloH * kQRowPitch;         // 43520
 constexpr int kQStageBytes = (kQHaloBytes + 1023) & ~1023;
 constexpr int kQStages = 2;
-constexpr int kQGroups = 3;                               // 512 threads -> 128 registers per thread, no spills
-constexpr int kQTmemCols = 512;                           // 3 accumulators x 128 columns, rounded up to a power of two
+constexpr int kQGroups = 2;                               // 384 threads; two tile epilogues in flight keep up with the MMAs
+constexpr int kQTmemCols = 256;                           // 2 accumulators x 128 columns
 constexpr int kQThreads = 128 + kQGroups * 128;
 constexpr int kQN = 128, kQK = 512;
 constexpr int kQWBytes = kQN * kQK * 2;                   // 131072
+constexpr int kQSkipW = 16, kQSkipH = kQTileH / 2 + 2;     // low-res skip patch: columns n0-4 .. n0+11 (TMA needs a 16-byte aligned start), rows m0-1 .. m0+16
+constexpr int kQSkipFloats = 3 * kQSkipH * kQSkipW;        // 864 floats = 3456 bytes per accumulator stage
+constexpr int kQSkipStride = (kQSkipFloats + 31) & ~31;    // buffers 128-byte aligned (TMA destination)
 constexpr int kQSmem = kQStages * kQStageBytes + kQWBytes + 1024;
 
 struct QuadParams {
   int B, H, W;
   int tiles_x, tiles_y, total_tiles;
   uint32_t idesc;
+  int has_skip;            // tmap_s is valid: the producer loads the low-res skip patch of every tile
   EpiParams e;
 };
 
@@ -61,7 +68,7 @@ __device__ __forceinline__ void quad_group_sync(int group) {
 
 __global__ void __launch_bounds__(kQThreads, 1)
 conv_tc_quad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                    const __grid_constant__ QuadParams p) {
+                    const __grid_constant__ CUtensorMap tmap_s, const __grid_constant__ QuadParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_w = smem + kQStages * kQStageBytes;
@@ -71,16 +78,19 @@ conv_tc_quad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __shared__ __align__(8) uint64_t tmem_full[kQGroups];
   __shared__ __align__(8) uint64_t tmem_empty[kQGroups];
   __shared__ __align__(8) uint64_t w_bar;
+  __shared__ __align__(8) uint64_t skip_full[kQGroups];
+  __shared__ __align__(128) float skip_smem[kQGroups * kQSkipStride];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_w);
+    if (p.has_skip) prefetch_tmap(&tmap_s);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kQStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < kQGroups; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+    for (int a = 0; a < kQGroups; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); mbar_init(&skip_full[a], 1); }
     mbar_init(&w_bar, 1);
     fence_barrier_init();
   }
@@ -112,6 +122,20 @@ conv_tc_quad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         mbar_expect_tx(&full_bar[stage], kQHaloBytes);
         tma_load_4d(smem + stage * kQStageBytes, &tmap_a, &full_bar[stage], 0, (x0 >> 1) - 1, y0 - 1, b);
         if (++stage == kQStages) { stage = 0; phase_bit ^= 1; }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== skip-patch producer: one small fp32 box per tile into its accumulator stage's buffer ====
+    if (lane == 0 && p.has_skip) {
+      int grp = 0;
+      uint32_t grp_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int x0, y0, b;
+        decode(tile, x0, y0, b);
+        mbar_wait(&tmem_empty[grp], grp_phase ^ 1);   // the stage's previous epilogue has finished with the buffer
+        mbar_expect_tx(&skip_full[grp], kQSkipFloats * 4);
+        tma_load_4d(skip_smem + grp * kQSkipStride, &tmap_s, &skip_full[grp], (x0 >> 1) - 4, (y0 >> 1) - 1, 0, b);
+        if (++grp == kQGroups) { grp = 0; grp_phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -187,77 +211,96 @@ conv_tc_quad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         staged_b = b;
       }
 
-      // ---- all global loads of the block before waiting for the accumulator ----
-      float nzq[4] = {0.f, 0.f, 0.f, 0.f};
+      // ---- global loads of the block (noise) before waiting for anything ----
+      float2 n01 = make_float2(0.f, 0.f), n23 = make_float2(0.f, 0.f);
+      if (ok && e.noise != nullptr) {
+        const float* np = e.noise + (int64_t)b * e.noise_bs + (int64_t)Y * p.W + X;
+        n01 = __ldg(reinterpret_cast<const float2*>(np));
+        n23 = __ldg(reinterpret_cast<const float2*>(np + p.W));
+      }
+
+      // ---- ToRGB tail: bias + 2x FIR up-sampling of the skip image for the four pixels of the block.  They share the
+      // 3x3 low-res patch around (m, n) = (Y/2, X/2): even outputs use rows m-1 (f0), m (f2), odd ones m (f1), m+1 (f3).
       float up[4][3];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) up[i][0] = up[i][1] = up[i][2] = 0.f;
-      if (ok) {
-        if (e.noise != nullptr) {
-          const float* np = e.noise + (int64_t)b * e.noise_bs + (int64_t)Y * p.W + X;
-          const float2 n01 = __ldg(reinterpret_cast<const float2*>(np));
-          const float2 n23 = __ldg(reinterpret_cast<const float2*>(np + p.W));
-          nzq[0] = nw * n01.x; nzq[1] = nw * n01.y; nzq[2] = nw * n23.x; nzq[3] = nw * n23.y;
-        }
-        if (e.fused_skip) {
-          // 2x FIR up-sampling of the skip image for the four pixels of the block: they share the 3x3 low-res
-          // patch around (m, n) = (Y/2, X/2); even outputs use rows m-1 (f0), m (f2), odd ones m (f1), m+1 (f3)
-          const int m = Y >> 1, n = X >> 1;
-          const float wy[2][3] = {{m > 0 ? e.fir[0] : 0.f, e.fir[2], 0.f}, {0.f, e.fir[1], m + 1 < h2 ? e.fir[3] : 0.f}};
-          const float wx[2][3] = {{n > 0 ? e.fir[0] : 0.f, e.fir[2], 0.f}, {0.f, e.fir[1], n + 1 < w2 ? e.fir[3] : 0.f}};
-          const int ym = max(m - 1, 0), yp = min(m + 1, h2 - 1), xm = max(n - 1, 0), xp = min(n + 1, w2 - 1);
+      for (int c = 0; c < 3; ++c) {
+        const float bias_c = e.fused_skip ? __ldg(e.rgb_bias + c) : 0.f;
+        up[0][c] = up[1][c] = up[2][c] = up[3][c] = bias_c;
+      }
+      if (p.has_skip) {
+        mbar_wait(&skip_full[group], grp_phase);
+        const float* sk = skip_smem + group * kQSkipStride + by * kQSkipW + bx + 3;   // patch origin = (m0 - 1, n0 - 4)
+        const float f0 = e.fir[0], f1 = e.fir[1], f2 = e.fir[2], f3 = e.fir[3];
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const float bias_c = __ldg(e.rgb_bias + c);
-            float pv[3][3];
-            if (e.skip_in != nullptr) {
-              const float* pl = e.skip_in + ((int64_t)b * 3 + c) * (plane >> 2);
-              const int ys[3] = {ym, m, yp}, xs[3] = {xm, n, xp};
+        for (int c = 0; c < 3; ++c) {
+          float h0[3], h1[3];   // horizontally filtered rows for even / odd output columns
 #pragma unroll
-              for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) pv[i][j] = __ldg(pl + (int64_t)ys[i] * w2 + xs[j]);
-            }
-#pragma unroll
-            for (int a = 0; a < 2; ++a)
-#pragma unroll
-              for (int bb = 0; bb < 2; ++bb) {
-                float acc = bias_c;
-                if (e.skip_in != nullptr) {
-#pragma unroll
-                  for (int i = 0; i < 3; ++i) {
-                    const float hrow = wx[bb][0] * pv[i][0] + wx[bb][1] * pv[i][1] + wx[bb][2] * pv[i][2];
-                    acc = fmaf(wy[a][i], hrow, acc);
-                  }
-                }
-                up[a * 2 + bb][c] = acc;
-              }
+          for (int i = 0; i < 3; ++i) {
+            const float* rowp = sk + (c * kQSkipH + i) * kQSkipW;
+            const float p0 = rowp[0], p1 = rowp[1], p2 = rowp[2];
+            h0[i] = fmaf(f0, p0, f2 * p1);
+            h1[i] = fmaf(f1, p1, f3 * p2);
           }
+          up[0][c] += fmaf(f0, h0[0], f2 * h0[1]);
+          up[1][c] += fmaf(f0, h1[0], f2 * h1[1]);
+          up[2][c] += fmaf(f1, h0[1], f3 * h0[2]);
+          up[3][c] += fmaf(f1, h1[1], f3 * h1[2]);
         }
       }
+      const float nzq[4] = {nw * n01.x, nw * n01.y, nw * n23.x, nw * n23.y};
 
       mbar_wait(&tmem_full[group], grp_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(group * kQN);
+      const bool want_out = ok && e.out != nullptr && e.s_next != nullptr;
+      const bool want_y = ok && e.y_out != nullptr;
+      const int64_t pix0 = ((int64_t)b * p.H + Y) * p.W + X;
       float rgb[4][3];
 #pragma unroll
-      for (int ph = 0; ph < 4; ++ph) {   // 32-column chunk ph = pixel (a, b) = (ph >> 1, ph & 1) of the block
-        uint32_t v[32];
-        tmem_ld32(taddr + ph * 32, v);
-        __nv_bfloat16* outc = nullptr;
-        __nv_bfloat16* yc = nullptr;
-        if (ok) {
-          const int64_t pix = ((int64_t)b * p.H + Y + (ph >> 1)) * p.W + X + (ph & 1);
-          if (e.out != nullptr && e.s_next != nullptr) outc = (__nv_bfloat16*)e.out + pix * 32;
-          if (e.y_out != nullptr) yc = (__nv_bfloat16*)e.y_out + pix * 32;
-        }
-        float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+      for (int ph = 0; ph < 4; ++ph) rgb[ph][0] = rgb[ph][1] = rgb[ph][2] = 0.f;
+#pragma unroll 1
+      for (int cg = 0; cg < 4; ++cg) {   // 8 channels x the 4 pixels (column chunks) of the block
+        uint32_t v[4][8];
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph) tmem_ld8(taddr + ph * 32 + cg * 8, v[ph]);
+        const float4 dA = *reinterpret_cast<const float4*>(s_d + cg * 8), dB = *reinterpret_cast<const float4*>(s_d + cg * 8 + 4);
+        const float4 bA = *reinterpret_cast<const float4*>(s_b + cg * 8), bB = *reinterpret_cast<const float4*>(s_b + cg * 8 + 4);
+        const float4 r0A = *reinterpret_cast<const float4*>(s_w + cg * 8), r0B = *reinterpret_cast<const float4*>(s_w + cg * 8 + 4);
+        const float4 r1A = *reinterpret_cast<const float4*>(s_w + 32 + cg * 8), r1B = *reinterpret_cast<const float4*>(s_w + 32 + cg * 8 + 4);
+        const float4 r2A = *reinterpret_cast<const float4*>(s_w + 64 + cg * 8), r2B = *reinterpret_cast<const float4*>(s_w + 64 + cg * 8 + 4);
+        const float dd[8] = {dA.x, dA.y, dA.z, dA.w, dB.x, dB.y, dB.z, dB.w};
+        const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+        const float w0[8] = {r0A.x, r0A.y, r0A.z, r0A.w, r0B.x, r0B.y, r0B.z, r0B.w};
+        const float w1[8] = {r1A.x, r1A.y, r1A.z, r1A.w, r1B.x, r1B.y, r1B.z, r1B.w};
+        const float w2[8] = {r2A.x, r2A.y, r2A.z, r2A.w, r2B.x, r2B.y, r2B.z, r2B.w};
         tmem_ld_wait();
-        epilogue_chunk32<EPI_ACT_RGB>(v, s_d, s_b, s_n, s_w, s_w + 32, s_w + 64, nzq[ph], false, r0, r1, r2, outc, yc);
-        rgb[ph][0] = r0; rgb[ph][1] = r1; rgb[ph][2] = r2;
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph) {
+          float x[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            x[j] = fmaf(__uint_as_float(v[ph][j]), dd[j], bb[j] + nzq[ph]);
+            x[j] = fmaxf(x[j], 0.2f * x[j]);
+            rgb[ph][0] = fmaf(w0[j], x[j], rgb[ph][0]);
+            rgb[ph][1] = fmaf(w1[j], x[j], rgb[ph][1]);
+            rgb[ph][2] = fmaf(w2[j], x[j], rgb[ph][2]);
+          }
+          if (want_out || want_y) {   // not taken for the last layer of the network (no next layer, inference)
+            const int64_t pix = pix0 + (ph >> 1) * (int64_t)p.W + (ph & 1);
+            if (want_y)
+              *reinterpret_cast<uint4*>((__nv_bfloat16*)e.y_out + pix * 32 + cg * 8) =
+                  make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+            if (want_out) {
+              const float4 nA = *reinterpret_cast<const float4*>(s_n + cg * 8), nB = *reinterpret_cast<const float4*>(s_n + cg * 8 + 4);
+              *reinterpret_cast<uint4*>((__nv_bfloat16*)e.out + pix * 32 + cg * 8) =
+                  make_uint4(pack_bf16(x[0] * nA.x, x[1] * nA.y), pack_bf16(x[2] * nA.z, x[3] * nA.w),
+                             pack_bf16(x[4] * nB.x, x[5] * nB.y), pack_bf16(x[6] * nB.z, x[7] * nB.w));
+            }
+          }
+        }
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty[group]);
+      mbar_arrive(&tmem_empty[group]);   // releases the accumulator stage and its skip patch buffer
       grp_phase ^= 1;
 
       if (e.wr != nullptr && ok) {
@@ -337,6 +380,16 @@ int launch_conv_tc_quad(const void* in, const __nv_bfloat16* w, const ConvGeom& 
     const uint32_t box[3] = {64, kQN, 1};
     L2I_TRY(make_tmap(&tw, w, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
   }
+  CUtensorMap ts = ta;   // placeholder when there is no skip image (first ToRGB of a network never reaches this kernel)
+  p.has_skip = (e.fused_skip && e.skip_in != nullptr) ? 1 : 0;
+  if (p.has_skip) {
+    const uint64_t h2 = (uint64_t)g.H / 2, w2 = (uint64_t)g.W / 2;
+    const uint64_t dims[4] = {w2, h2, 3, (uint64_t)g.B};
+    const uint64_t str[4] = {4, w2 * 4, h2 * w2 * 4, 3 * h2 * w2 * 4};
+    const uint32_t box[4] = {kQSkipW, kQSkipH, 3, 1};
+    if ((uintptr_t)e.skip_in % 16 != 0 || (w2 * 4) % 16 != 0) { set_error("conv_tc_quad: skip image must be 16-byte aligned"); return L2I_ERR_INVALID_ARG; }
+    L2I_TRY(make_tmap_f32(&ts, e.skip_in, 4, dims, str, box));
+  }
   p.tiles_x = ceil_div(g.W, kQTileW); p.tiles_y = ceil_div(g.H, kQTileH);
   const int64_t total = (int64_t)p.tiles_x * p.tiles_y * g.B;
   if (total <= 0 || total > 0x7fffffff) { set_error("conv_tc_quad: bad tile count"); return L2I_ERR_INVALID_ARG; }
@@ -347,7 +400,7 @@ int launch_conv_tc_quad(const void* in, const __nv_bfloat16* w, const ConvGeom& 
     attr_set = true;
   }
   const int grid = std::min(p.total_tiles, kNumSMs);
-  conv_tc_quad_kernel<<<grid, kQThreads, kQSmem, st>>>(ta, tw, p);
+  conv_tc_quad_kernel<<<grid, kQThreads, kQSmem, st>>>(ta, tw, ts, p);
   return check_launch("conv_tc_quad");
 }
 
