@@ -36,8 +36,8 @@ UNIT = "images/s"
 def _args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=1024)
     ap.add_argument("--batch", type=int, default=32, help="latent samples per GPU per step")
@@ -69,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -281,13 +281,33 @@ def run_ours(args):
     blur_ms, blur_by = sum(v["ms"] for v in blur), sum(v["bytes"] for v in blur)
     seg_ms = sum(v["ms"] for v in table.values())
     achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-    roofline = {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM modulated conv, all %d launches of a step)" % len(conv)
+    # DRAM traffic of the same launches from the committed ncu --set full capture (profiles/), per step like `achieved`
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath) and args.dtype == "bf16" and size == 1024:
+        tj = json.load(open(tpath))
+        traffic = tj.get("conv_dram_bytes_per_image", 0.0) * b
+        traffic_src = tj.get("source")
+    # per-layer roofline: each conv segment against max(tensor time, HBM time) of its ALGORITHMIC flops / bytes
+    layers, ideal_ms = [], 0.0
+    for name, v in table.items():
+        if v["kind"] not in (0, 1) or v["ms"] <= 0:
+            continue
+        t_tensor = v["flops"] / (peaks["tflops"] * 1e12) * 1e3
+        t_hbm = v["bytes"] / (peaks["hbm_gbs"] * 1e9) * 1e3
+        ideal = max(t_tensor, t_hbm)
+        ideal_ms += ideal
+        layers.append({"layer": name, "ms": round(v["ms"], 4), "tflops": round(v["flops"] / v["ms"] / 1e9, 1),
+                       "gbs": round(v["bytes"] / v["ms"] / 1e6, 1), "bound": "tensor" if t_tensor >= t_hbm else "hbm",
+                       "frac": round(ideal / v["ms"], 3)})
+    roofline = {"kernel": "tcgen05 implicit-GEMM modulated convs (conv_tc / conv_tc_halo / conv_tc_quad, all %d launches of a step)" % len(conv)
                 if args.dtype == "bf16" else "conv_simt_kernel", "bound": "tensor", "achieved": achieved,
-                "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": None,
-                "peak_source": peaks["source"], "launch_ms_total": conv_ms, "share_of_step": conv_ms / seg_ms if seg_ms else None,
-                "algorithmic_gflop_per_step": conv_fl / 1e9}
+                "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": traffic,
+                "traffic_source": traffic_src, "peak_source": peaks["source"], "launch_ms_total": conv_ms,
+                "share_of_step": conv_ms / seg_ms if seg_ms else None, "algorithmic_gflop_per_step": conv_fl / 1e9,
+                "speed_of_light_frac": (ideal_ms / (conv_ms + blur_ms)) if (conv_ms + blur_ms) > 0 else None}
     blur_gbs = blur_by / (blur_ms * 1e-3) / 1e9 if blur_ms > 0 else 0.0
-    roofline_hbm = {"kernel": "blur_act_kernel (FIR blur + noise + bias + lrelu + next-style scale)", "bound": "hbm",
+    roofline_hbm = {"kernel": "blur_act_kernel (FIR blur + noise + bias + lrelu + next-style scale; layers below 256 px)", "bound": "hbm",
                     "achieved": blur_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": blur_gbs / peaks["hbm_gbs"],
                     "traffic": None, "launch_ms_total": blur_ms, "share_of_step": blur_ms / seg_ms if seg_ms else None}
     if args.profile_json and rank == 0:
@@ -319,6 +339,7 @@ def run_ours(args):
         "e2e": {"value": images / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
                 "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm,
+        "roofline_layers": layers,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)

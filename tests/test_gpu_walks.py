@@ -98,3 +98,70 @@ def test_walk_pickle_roundtrip_under_reference_module_path(tmp_path):
     torch.save(walk, p)
     back = torch.load(p, weights_only=False)
     assert torch.equal(back.w, walk.w)
+
+
+def test_walk_trainer_step_matches_oracle_autograd():
+    """One train.py-style step (G fwd no-grad, R, eps, walk, G fwd+bwd, BCE, Adam) through WalkTrainer:
+    the walk-parameter gradient equals autograd through the float64 oracle with the same (tiny) regressor."""
+    from latent2im_b200.graphs.stylegan_v2_real.networks import Generator
+    from latent2im_b200.graphs.stylegan_v2_real.transform_base import WalkLinearMultiW
+    from latent2im_b200.synthetic import load_synthetic, synthetic_noise, synthetic_walk_w, synthetic_z
+    from latent2im_b200.train_step import WalkTrainer, bce_clamped
+    from oracle import GeneratorSpec, generator_forward_ref, mapping_ref
+    from oracle.walks import walk_linear_ref
+
+    size, dim, n_mlp, batch = 16, 32, 2, 3
+    spec = GeneratorSpec(size=size, style_dim=dim, n_mlp=n_mlp)
+    gen = load_synthetic(Generator(size, dim, n_mlp), seed=0)
+    sd = {k: v.double() for k, v in gen.state_dict().items()}
+    gen = gen.cuda().eval()
+    gen.set_native(dtype=torch.float32, max_batch=batch)
+    torch.manual_seed(1)
+    reg = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3, padding=1), torch.nn.Tanh(), torch.nn.AdaptiveAvgPool2d(1),
+                              torch.nn.Flatten(), torch.nn.Linear(4, 5), torch.nn.Sigmoid())
+    reg64 = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3, padding=1), torch.nn.Tanh(), torch.nn.AdaptiveAvgPool2d(1),
+                                torch.nn.Flatten(), torch.nn.Linear(4, 5), torch.nn.Sigmoid()).double()
+    reg64.load_state_dict({k: v.double() for k, v in reg.state_dict().items()})
+    reg = reg.cuda()
+    walk = WalkLinearMultiW(dim, spec.log_size - 2, 1, ["Smiling"]).cuda()
+    w0 = synthetic_walk_w(1, spec.n_latent, dim, seed=0)
+    with torch.no_grad():
+        walk.w.copy_(w0.cuda())
+    z = torch.tensor(synthetic_z(batch, 0, dim), dtype=torch.float32)
+    target = torch.full((batch, 1), 0.8)
+    noise = synthetic_noise(spec.num_layers, batch)
+
+    # product path, with explicit noise so that both G forwards are reproducible: patch the generator call
+    trainer = WalkTrainer(gen, walk, reg, [2], lr=1e-3)
+    orig_forward = gen.forward
+    gen.forward = lambda styles, **kw: orig_forward(styles, noise=[n.cuda() for n in noise], **kw)
+    loss = trainer.step(z.cuda(), target.cuda())
+    g_native = None
+    # the optimizer already stepped: recover the gradient from a fresh backward at the ORIGINAL parameters
+    with torch.no_grad():
+        walk.w.copy_(w0.cuda())
+    walk.w.grad = None
+    w = gen.style(z.cuda())
+    with torch.no_grad():
+        img0, _ = gen(w[:, None, :].expand(-1, spec.n_latent, -1), input_is_latent=True)
+        eps = target.cuda() - reg(img0)[:, [2]]
+    lat = torch.stack(walk([w] * spec.n_latent, eps), 1)
+    img, _ = gen(lat, input_is_latent=True)
+    loss2 = bce_clamped(reg(img)[:, [2]], target.cuda())
+    loss2.backward()
+    g_native = walk.w.grad.detach().cpu().double()
+    assert abs(loss.item() - loss2.item()) <= 1e-5 * max(1.0, abs(loss2.item()))
+
+    # oracle (float64, CPU autograd)
+    wr = mapping_ref(sd, z.double(), spec)
+    with torch.no_grad():
+        img0r = generator_forward_ref(sd, wr[:, None, :].repeat(1, spec.n_latent, 1), noise, spec)
+        epsr = target.double() - reg64(img0r)[:, [2]]
+    wp = w0.double().clone().requires_grad_(True)
+    latr = torch.stack(walk_linear_ref([wr] * spec.n_latent, epsr, wp), 1)
+    imgr = generator_forward_ref(sd, latr, noise, spec)
+    lossr = bce_clamped(reg64(imgr)[:, [2]], target.double())
+    (g_ref,) = torch.autograd.grad(lossr, wp)
+    assert abs(loss2.item() - lossr.item()) <= 1e-3 * max(1.0, abs(lossr.item()))
+    scale = g_ref.abs().max().item()
+    assert (g_native - g_ref).abs().max().item() <= 5e-3 * scale, ((g_native - g_ref).abs().max().item(), scale)
