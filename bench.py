@@ -216,13 +216,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, after=None):
         barrier()
         l0 = nt.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for s in range(steps):
             fn(s)
+        if after is not None:
+            after()          # e.g. make the timing stream wait for the last asynchronous device->host copy
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -255,7 +257,7 @@ def run_ours(args):
 
     for s in range(min(args.warmup, 3)):
         step_e2e(s)
-    ms_e2e, _ = timed(step_e2e, args.steps)
+    ms_e2e, _ = timed(step_e2e, args.steps, after=pipe.join)
 
     # ---- per-segment device timing of the same step (roofline of the dominant kernel) ---------
     h = gen._handle(dev, b)

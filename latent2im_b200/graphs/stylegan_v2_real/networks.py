@@ -350,15 +350,16 @@ class Generator(nn.Module):
             out.append(n.detach().to(device=device, dtype=torch.float32).contiguous())
         return out
 
-    def synthesize(self, latent, noise=None, randomize_noise=True, want_uint8=False, want_float=True):
+    def synthesize(self, latent, noise=None, randomize_noise=True, want_uint8=False, want_float=True, out_uint8=None):
         if torch.is_grad_enabled() and latent.requires_grad:
             if want_uint8:
                 raise RuntimeError("the uint8 image is not differentiable; call synthesize under torch.no_grad()")
             nz = self._noise_list(latent.shape[0], latent.device, noise, randomize_noise)
             return _SynthesisFn.apply(latent, self, nz)
-        return self._synthesize(latent, noise, randomize_noise, want_uint8, want_float, training=False)
+        return self._synthesize(latent, noise, randomize_noise, want_uint8, want_float, training=False, out_uint8=out_uint8)
 
-    def _synthesize(self, latent, noise=None, randomize_noise=True, want_uint8=False, want_float=True, training=False):
+    def _synthesize(self, latent, noise=None, randomize_noise=True, want_uint8=False, want_float=True, training=False,
+                    out_uint8=None):
         """``latent`` [B, n_latent, D] -> image [B, 3, size, size] float32 (and / or the uint8 NHWC
         image ``clip((x + 1) / 2 * 255)`` the reference computes on the host, transform_base.py:625-626)."""
         device = latent.device
@@ -373,7 +374,11 @@ class Generator(nn.Module):
         nz_ptrs = (C.c_void_p * self.num_layers)(*[n.data_ptr() for n in nz])
         nz_batch = (C.c_int * self.num_layers)(*[n.shape[0] for n in nz])
         image = torch.empty(batch, 3, self.size, self.size, device=device, dtype=torch.float32) if want_float else None
-        image_u8 = torch.empty(batch, self.size, self.size, 3, device=device, dtype=torch.uint8) if want_uint8 else None
+        image_u8 = None
+        if want_uint8:
+            image_u8 = out_uint8 if out_uint8 is not None else torch.empty(batch, self.size, self.size, 3, device=device, dtype=torch.uint8)
+            if image_u8.shape != (batch, self.size, self.size, 3) or image_u8.dtype != torch.uint8 or not image_u8.is_contiguous():
+                raise RuntimeError("out_uint8 must be a contiguous uint8 tensor of shape [B, size, size, 3]")
         with torch.cuda.device(device):
             if training or h.training:
                 nt.check(h.lib.l2i_generator_set_training(h.handle, 1 if training else 0), "generator_set_training")

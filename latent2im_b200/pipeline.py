@@ -5,8 +5,9 @@ This is the call a user of the accelerated path makes for the forward-only edit 
 i.e. the body of the reference's ``apply_alpha`` + the host-side ``clip((x+1)/2*255)`` of
 ``vis_multi_image_batch_alphas`` (transform_base.py:554-603, 625-626) with the attribute regressor
 factored out (``alpha`` is the walk step epsilon).  Host buffers are
-pinned once; every call copies z / alpha to the device and the uint8 result back on the current
-stream.
+pinned once; every call copies z / alpha to the device on the current stream and the uint8 result
+back on a dedicated copy stream (double-buffered), so the 3 MB/image device->host transfer of step i
+overlaps the kernels of step i+1.
 """
 from __future__ import annotations
 
@@ -23,7 +24,11 @@ class EditPipeline:
         dim, size = generator.style_dim, generator.size
         self.z_host = torch.empty(batch, dim, dtype=torch.float32).pin_memory()
         self.alpha_host = torch.empty(batch, n_attr, dtype=torch.float32).pin_memory()
-        self.out_host = torch.empty(batch, size, size, 3, dtype=torch.uint8).pin_memory()
+        self.out_hosts = [torch.empty(batch, size, size, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.out_devs = [torch.empty(batch, size, size, 3, dtype=torch.uint8, device=self.device) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.copy_done = [None, None]      # event: device->host copy out of buffer k has finished
+        self._k = 0
         self.z_dev = torch.empty(batch, dim, dtype=torch.float32, device=self.device)
         self.alpha_dev = torch.empty(batch, n_attr, dtype=torch.float32, device=self.device)
         generator.set_native(max_batch=batch)
@@ -34,16 +39,16 @@ class EditPipeline:
 
     @property
     def d2h_bytes(self) -> int:
-        return self.out_host.numel()
+        return self.out_hosts[0].numel()
 
     @torch.no_grad()
-    def edit_device(self, z_dev, alpha_dev, layers=None, noise=None, want_uint8=False):
+    def edit_device(self, z_dev, alpha_dev, layers=None, noise=None, want_uint8=False, out_uint8=None):
         """Device-resident part: mapping -> walk -> synthesis.  Returns the fp32 image (reference
         return value) or the uint8 NHWC image."""
         w = self.gen.style(z_dev)
         ws = self.walk([w] * self.gen.n_latent, alpha_dev, layers=layers)
         latent = torch.stack(ws, 1) if not _is_block(ws) else ws[0]._base
-        return self.gen.synthesize(latent, noise=noise, want_uint8=want_uint8, want_float=not want_uint8)
+        return self.gen.synthesize(latent, noise=noise, want_uint8=want_uint8, want_float=not want_uint8, out_uint8=out_uint8)
 
     @torch.no_grad()
     def edit(self, z, alpha, layers=None, noise=None, sync=True) -> np.ndarray:
@@ -51,13 +56,38 @@ class EditPipeline:
         float32 exactly like ``torch.Tensor(z)`` in train.py:56); ``alpha``: [B, A] host."""
         self.z_host.copy_(torch.as_tensor(z).to(torch.float32))
         self.alpha_host.copy_(torch.as_tensor(alpha).to(torch.float32).reshape(self.batch, -1))
+        main = torch.cuda.current_stream(self.device)
+        k = self._k
+        self._k ^= 1
+        if self.copy_done[k] is not None:
+            main.wait_event(self.copy_done[k])           # buffer k is free again (copy of two calls ago)
         self.z_dev.copy_(self.z_host, non_blocking=True)
         self.alpha_dev.copy_(self.alpha_host, non_blocking=True)
-        u8 = self.edit_device(self.z_dev, self.alpha_dev, layers=layers, noise=noise, want_uint8=True)
-        self.out_host.copy_(u8, non_blocking=True)
+        self.edit_device(self.z_dev, self.alpha_dev, layers=layers, noise=noise, want_uint8=True, out_uint8=self.out_devs[k])
+        computed = torch.cuda.Event()
+        computed.record(main)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(computed)
+            self.out_hosts[k].copy_(self.out_devs[k], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.copy_stream)
+        self.copy_done[k] = done
         if sync:
-            torch.cuda.current_stream(self.device).synchronize()
-        return self.out_host.numpy()
+            done.synchronize()
+        return self.out_hosts[k].numpy()
+
+    def join(self):
+        """Makes the current stream wait for every outstanding device->host copy (no host blocking)."""
+        main = torch.cuda.current_stream(self.device)
+        for ev in self.copy_done:
+            if ev is not None:
+                main.wait_event(ev)
+
+    def wait(self):
+        """Blocks until every outstanding device->host copy has landed."""
+        for ev in self.copy_done:
+            if ev is not None:
+                ev.synchronize()
 
 
 def _is_block(ws) -> bool:
