@@ -245,7 +245,26 @@ __global__ void pack_weight_t_kernel(float* __restrict__ dst, const float* __res
     for (int t = 0; t < ntap; ++t) dst[(int64_t)t * total + idx] = src[idx * ntap + t] * scale;
 }
 
+// dst [tap][Cin][Cout] bf16 = scale * src[Cout][Cin][tap]   (K-major B operand of the data-gradient GEMM)
+__global__ void pack_weight_t_bf16_kernel(__nv_bfloat16* __restrict__ dst, const float* __restrict__ src, int Cout, int Cin,
+                                          int ntap, float scale) {
+  const int64_t total = (int64_t)Cout * Cin;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(idx % Cin), co = (int)(idx / Cin);
+    for (int t = 0; t < ntap; ++t) dst[((int64_t)t * Cin + ci) * Cout + co] = __float2bfloat16_rn(src[idx * ntap + t] * scale);
+  }
+}
+
 namespace {
+
+// data-gradient conv: tcgen05 kernel for bf16 (raw epilogue, no demodulation), CUDA-core kernel otherwise
+template <typename T>
+int run_dgrad_conv(l2i_generator* g, const StyledConvLayer& L, const void* in, const ConvGeom& geom, const EpiParams& e,
+                   cudaStream_t st) {
+  if (sizeof(T) == 2 && g->conv_impl != 1 && L.w_bf16_t != nullptr && conv_tc_supported(geom, e))
+    return launch_conv_tc(in, L.w_bf16_t, geom, e, st);
+  return launch_conv_simt<T>(in, L.w_f32_t, geom, e, st);
+}
 
 template <typename T>
 int launch_act_bwd(void* g_out, const void* g_xn, const float* g_rgb, const void* y, const float* s_next, int64_t s_next_bs,
@@ -336,7 +355,7 @@ int backward_impl(l2i_generator* g, float* grad_latent, const float* grad_image,
                                 next ? g->R_s + L.d_off : nullptr, g->R_d + L.d_off, R_bs, g->R_rgb + R.wr_off, Rr_bs, B, HWo,
                                 L.cout, st));
       geom.H = geom.W = L.res_out; geom.in_scale = 1; geom.taps[0] = dgrad_plain_taps();
-      L2I_TRY(launch_conv_simt<T>(g->gbuf, L.w_f32_t, geom, e, st));
+      L2I_TRY(run_dgrad_conv<T>(g, L, g->gbuf, geom, e, st));
       // skip chain: g_skip(res/2) = Upsample^T(g_skip(res)) = upfirdn2d(down=2, flipped kernel, pad (1,1))
       if (rgb_i > 0) {
         float* dst = g->gskip[gskip_sel];
@@ -354,7 +373,7 @@ int backward_impl(l2i_generator* g, float* grad_latent, const float* grad_image,
       L2I_TRY((launch_blur_bwd<T, TIN>(g->tbuf, g->gbuf, L.t_save, demod, g->d_rows, g->R_d + L.d_off, R_bs, B, L.res_out,
                                        L.res_out, TH, TH, L.cout, g->fir, st)));
       geom.H = geom.W = TH; geom.in_scale = 2; geom.taps[0] = dgrad_up_taps();
-      L2I_TRY(launch_conv_simt<T>(g->tbuf, L.w_f32_t, geom, e, st));
+      L2I_TRY(run_dgrad_conv<T>(g, L, g->tbuf, geom, e, st));
     }
     g_xn = gx_dst;
     gx_sel ^= 1;
@@ -409,6 +428,7 @@ extern "C" int l2i_generator_set_training(l2i_generator_t* g, int enable) {
         L.t_save = p;
       }
       L2I_TRY(train_alloc(g, &L.w_f32_t, (int64_t)9 * L.cin * L.cout));
+      if (g->dtype == L2I_BF16) L2I_TRY(train_alloc(g, &L.w_bf16_t, (int64_t)9 * L.cin * L.cout));
       act_elems = std::max(act_elems, B * L.res_out * L.res_out * (int64_t)L.cout);
     }
     char* gb = nullptr;
@@ -445,6 +465,10 @@ extern "C" int l2i_generator_set_training(l2i_generator_t* g, int enable) {
     const int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)kNumSMs * 8);
     pack_weight_t_kernel<<<blocks, 256>>>(L.w_f32_t, g->params.at(L.name + ".conv.weight").ptr, L.cout, L.cin, 9, scale);
     L2I_TRY(check_launch("pack_weight_t"));
+    if (L.w_bf16_t != nullptr) {
+      pack_weight_t_bf16_kernel<<<blocks, 256>>>(L.w_bf16_t, g->params.at(L.name + ".conv.weight").ptr, L.cout, L.cin, 9, scale);
+      L2I_TRY(check_launch("pack_weight_t_bf16"));
+    }
   }
   L2I_CUDA_TRY(cudaDeviceSynchronize());
   g->training = true;

@@ -31,6 +31,7 @@ struct TcParams {
   uint32_t a_bytes;               // bytes one A box load delivers (bw*bh*BLOCK_K*2)
   uint32_t idesc;                 // UMMA instruction descriptor (operand formats chosen on the host)
   int weight_taps;                // 9 or 18 tap slices in the weight tensor
+  int in_scale;                   // 1, or 2: tap-shifted A boxes step over every other input pixel (strided TMA box)
   int up_cout;                    // composite up-conv: real Cout (GEMM N = 4 * up_cout = (phase, co)); 0 otherwise
   int pair_out;                   // composite: pair-packed output for the following Cin == 32 halo layer
   EpiParams e;
@@ -127,7 +128,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             uint8_t* sa = smem + stage * L::kStageBytes;
             uint8_t* sb = sa + L::kABytes;
             mbar_expect_tx(&full_bar[stage], tx_bytes);
-            tma_load_4d(sa, &tmap_a, &full_bar[stage], kc * BLOCK_K, x0 + taps.dx[t], y0 + taps.dy[t], b);
+            tma_load_4d(sa, &tmap_a, &full_bar[stage], kc * BLOCK_K, x0 * p.in_scale + taps.dx[t], y0 * p.in_scale + taps.dy[t], b);
             tma_load_3d(sb, &tmap_b, &full_bar[stage], kc * BLOCK_K, nt * BLOCK_N, taps.wtap[t]);
             if (++stage == STAGES) { stage = 0; phase_bit ^= 1; }
           }
@@ -330,7 +331,13 @@ EncodeTiledFn get_encode_fn() {
 
 namespace tc {
 static int make_tmap_typed(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
-                           const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
+                           const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz,
+                           const uint32_t* elem_strides = nullptr);
+
+int make_tmap_strided(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, const uint32_t* elem_strides, CUtensorMapSwizzle swz) {
+  return make_tmap_typed(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, swz, elem_strides);
+}
 
 int make_tmap(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
               const uint32_t* box, CUtensorMapSwizzle swz) {
@@ -343,7 +350,8 @@ int make_tmap_f32(CUtensorMap* map, const void* base, int rank, const uint64_t* 
 }
 
 static int make_tmap_typed(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
-                           const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
+                           const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz,
+                           const uint32_t* elem_strides) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("conv_tc: cuTensorMapEncodeTiled entry point not available");
@@ -351,7 +359,7 @@ static int make_tmap_typed(CUtensorMap* map, CUtensorMapDataType dt, const void*
   }
   cuuint64_t gdim[5], gstr[4];
   cuuint32_t bx[5], es[5];
-  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = elem_strides ? elem_strides[i] : 1; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i + 1];
   CUresult r = fn(map, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -377,8 +385,10 @@ int launch_variant_epi(const void* in, const __nv_bfloat16* w, TcParams& p, cuda
   {
     const uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.B};
     const uint64_t str[4] = {2, (uint64_t)p.Cin * 2, (uint64_t)p.W * p.Cin * 2, (uint64_t)p.H * p.W * p.Cin * 2};
-    const uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)p.bw, (uint32_t)p.bh, 1u};
-    L2I_TRY(make_tmap(&ta, in, 4, dims, str, box, swz));
+    const uint32_t sc = (uint32_t)p.in_scale;   // in_scale 2: the box traverses every other pixel (data gradient of the stride-2 conv)
+    const uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)p.bw * sc, (uint32_t)p.bh * sc, 1u};
+    const uint32_t estr[4] = {1u, sc, sc, 1u};
+    L2I_TRY(make_tmap_strided(&ta, in, 4, dims, str, box, estr, swz));
   }
   {
     const uint64_t dims[3] = {(uint64_t)p.Cin, (uint64_t)p.Cout, (uint64_t)p.weight_taps};
@@ -410,7 +420,7 @@ int pick_block_n(int cout) { return cout >= 256 ? 256 : cout; }
 
 bool conv_tc_supported(const ConvGeom& g, const EpiParams& e) {
   (void)e;
-  if (g.in_scale != 1) return false;  // strided-input data gradient runs on the CUDA-core kernel
+  if (g.in_scale != 1 && g.in_scale != 2) return false;
   if (g.Cin % 32 != 0 || g.Cin < 32) return false;
   const int bn = pick_block_n(g.Cout);
   if (!(bn == 32 || bn == 64 || bn == 128 || bn == 256)) return false;
@@ -443,6 +453,7 @@ int launch_conv_tc(const void* in, const __nv_bfloat16* w, const ConvGeom& g, co
   p.weight_taps = g.weight_taps > 0 ? g.weight_taps : 9;
   p.up_cout = g.up_cout;
   p.pair_out = g.out_pair_packed;
+  p.in_scale = g.in_scale > 0 ? g.in_scale : 1;
   if (g.up_cout > 0 && (g.Cout != 4 * g.up_cout || g.up_cout % 32 != 0 || g.nphase != 1 || e.mode != 0 || e.wr != nullptr ||
                         (g.out_pair_packed && g.up_cout != 32))) {
     set_error("conv_tc: bad composite up-conv configuration (Cout=%d up_cout=%d)", g.Cout, g.up_cout);

@@ -40,6 +40,7 @@ struct HaloParams {
   int out_H, out_W;
   int tiles_x, tiles_y, total_tiles;
   uint32_t idesc;
+  int tma_store;           // composite: write the output through per-warp SWIZZLE_64B staging tiles + strided TMA stores
   int base_offset_mode;    // debug only; measured on B200: the swizzle follows absolute smem address bits, so tap-shifted
                            // start addresses need base_offset = 0 (setting (start >> 7) & 7 gives wrong results)
   EpiParams e;
@@ -47,11 +48,9 @@ struct HaloParams {
 
 namespace {
 
-constexpr int kHaloW = 16, kHaloH = 18;                 // halo tile in units
-constexpr int kHaloBytes = kHaloW * kHaloH * 128;       // 36864
+constexpr int kHaloH = 18;                              // halo tile rows (units); its width HW is 16 (power-of-two pitch) or 10
 constexpr int kTileW = 8, kTileH = 16;
-constexpr int kGroups = 4;
-constexpr int kThreads = 128 + kGroups * 128;
+constexpr int halo_stage_bytes(int hw) { return (hw * kHaloH * 128 + 1023) & ~1023; }   // 36864 / 23552
 
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t addr, uint32_t sbo_bytes, uint32_t base_offset) {
   uint64_t d = 0;
@@ -77,21 +76,27 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, u
 
 // N = GEMM N (Cout, or 4 * Cout for the composite up-conv), STAGES = A halo stages, PAIR = Cin 32 pair-packed
 // units, COMP = composite up-conv (N = 4 phases x 32 channels, fused blur: SURVEY 0.6b), EPI = fused epilogue kind
-template <int N, int STAGES, int NACC, bool PAIR, bool COMP, int EPI>
-__global__ void __launch_bounds__(kThreads, 1)
+// HW = halo tile width in units (the UMMA 8-row-group stride is HW * 128 bytes), kGroups = epilogue warpgroups
+template <int N, int STAGES, int NACC, bool PAIR, bool COMP, int EPI, int HW, int kGroups>
+__global__ void __launch_bounds__(128 + kGroups * 128, 1)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                    const __grid_constant__ HaloParams p) {
+                    const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ HaloParams p) {
+  constexpr int kHaloW = HW;
+  constexpr int kHaloBytes = HW * kHaloH * 128;            // bytes one halo box load delivers
+  constexpr int kStageBytes = halo_stage_bytes(HW);
+  constexpr int kTmemAlloc = kGroups * NACC * N <= 32 ? 32 : (kGroups * NACC * N <= 64 ? 64 : (kGroups * NACC * N <= 128 ? 128 : (kGroups * NACC * N <= 256 ? 256 : 512)));
   constexpr int kWTileBytes = N * 128;
-  constexpr int kTmemCols = kGroups * NACC * N;
-  static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM budget");
+  constexpr int kTmemCols = kTmemAlloc;
+  static_assert(kGroups * NACC * N <= 512, "TMEM budget");
   constexpr int CO = COMP ? N / 4 : N;   // distinct output channels whose epilogue vectors are staged
   constexpr int kEpiFloats = 6 * CO;
   static_assert(!COMP || (CO == 32 && NACC == 1 && EPI == EPI_ACT), "composite variant: 4 phases x 32 channels in one accumulator");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // A halo stages, then the resident weights
-  uint8_t* smem_w = smem + STAGES * kHaloBytes;
+  uint8_t* smem_w = smem + STAGES * kStageBytes;
   const int wbytes = p.nwtiles * kWTileBytes;
+  uint8_t* smem_stage_out = smem_w + ((wbytes + 1023) & ~1023);   // composite + tma_store: 2 KB per epilogue warp
   __shared__ __align__(16) float epi_smem[kGroups * kEpiFloats];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
@@ -104,6 +109,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_w);
+    if (COMP && p.tma_store) prefetch_tmap(&tmap_o);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -137,7 +143,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         decode(tile, x0, y0, b);
         mbar_wait(&empty_bar[stage], phase_bit ^ 1);
         mbar_expect_tx(&full_bar[stage], kHaloBytes);
-        tma_load_4d(smem + stage * kHaloBytes, &tmap_a, &full_bar[stage], 0, x0 - 1, y0 - 1, b);
+        tma_load_4d(smem + stage * kStageBytes, &tmap_a, &full_bar[stage], 0, x0 - 1, y0 - 1, b);
         if (++stage == STAGES) { stage = 0; phase_bit ^= 1; }
       }
     }
@@ -155,7 +161,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         mbar_wait(&tmem_empty[grp], grp_phase ^ 1);
         mbar_wait(&full_bar[stage], phase_bit);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + stage * kHaloBytes);
+        const uint32_t a_base = smem_u32(smem + stage * kStageBytes);
         const uint32_t tmem_d = tmem_base + (uint32_t)(grp * NACC * N);
         uint32_t started = 0;  // accumulators that already received their first MMA
         for (int t = 0; t < p.ntaps; ++t) {
@@ -194,6 +200,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int64_t plane = (int64_t)p.out_H * p.out_W;
     const int lx = row & 7, ly = row >> 3;
     const bool raw_fp16 = e.raw_fp16 != 0;
+    const bool use_tma_store = COMP && p.tma_store != 0;
+    __nv_bfloat16* stage_out = (__nv_bfloat16*)(smem_stage_out + (warp - 4) * 2048) + lane * 32;   // this lane's 64-byte slot
+    const int stage_swz = (lane >> 1) & 3;                                                       // SWIZZLE_64B: chunk ^= address bits [7:8]
     uint32_t grp_phase = 0;
     int staged_b = -1;
     int it = 0;
@@ -279,6 +288,20 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (COMP) {                          // chunk = output phase
             const int phc = c0 >> 5;
             nzc = phc == 0 ? nzq[0] : (phc == 1 ? nzq[1] : (phc == 2 ? nzq[2] : nzq[3]));
+            if (use_tma_store) {
+              // the warp's 4 x 8 input pixels -> output pixels (2oy+py, 2ox+px): stage them as a [4][8][32] bf16 tile and let
+              // one strided TMA tensor store write it (full sectors, no LSU store wavefronts)
+              if (lane == 0) tma_store_wait_read();   // the previous store has finished reading the staging tile
+              __syncwarp();
+              tmem_ld_wait();
+              epilogue_chunk32<EPI>(v, s_d, s_b, s_n, s_w, s_w + CO, s_w + 2 * CO, nzc, raw_fp16, rgb0, rgb1, rgb2, stage_out,
+                                    nullptr, stage_swz);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0)
+                tma_store_4d(&tmap_o, smem_stage_out + (warp - 4) * 2048, 0, 2 * x0 + (phc & 1), 2 * (y0 + 4 * q) + (phc >> 1), b);
+              continue;
+            }
             if (ok[a]) {
               const int Xc = Xs[a] + (phc & 1);
               const int64_t pixc = ((int64_t)b * p.out_H + Ys[a] + (phc >> 1)) * p.out_W + Xc;
@@ -308,6 +331,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   }
 
+  if (COMP && p.tma_store && warp >= 4 && lane == 0) tma_store_wait_all();   // outstanding bulk stores must land before exit
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -316,22 +340,24 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
-template <int N, int STAGES, int NACC, bool PAIR, bool COMP, int EPI>
-int launch_halo_variant(const CUtensorMap& ta, const CUtensorMap& tw, const HaloParams& p, cudaStream_t st) {
-  const int wbytes = p.nwtiles * N * 128;
-  const int smem = STAGES * kHaloBytes + wbytes + 1024;   // + alignment slack; epilogue vectors and barriers are static
+template <int N, int STAGES, int NACC, bool PAIR, bool COMP, int EPI, int HW, int kGroups>
+int launch_halo_variant(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const HaloParams& p, cudaStream_t st) {
+  const int wbytes = (p.nwtiles * N * 128 + 1023) & ~1023;
+  // + alignment slack; epilogue vectors and barriers are static; composite: 2 KB output staging tile per epilogue warp
+  const int smem = STAGES * halo_stage_bytes(HW) + wbytes + 1024 + (COMP ? kGroups * 4 * 2048 : 0);
+  constexpr int kThreads = 128 + kGroups * 128;
   if (smem > 227 * 1024) {
     set_error("conv_tc_halo: shared memory budget exceeded (%d bytes)", smem);
     return L2I_ERR_UNSUPPORTED;
   }
-  auto kern = conv_tc_halo_kernel<N, STAGES, NACC, PAIR, COMP, EPI>;
+  auto kern = conv_tc_halo_kernel<N, STAGES, NACC, PAIR, COMP, EPI, HW, kGroups>;
   static int attr_smem = 0;
   if (attr_smem < smem) {
     L2I_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem = smem;
   }
   const int grid = std::min(p.total_tiles, kNumSMs);
-  kern<<<grid, kThreads, smem, st>>>(ta, tw, p);
+  kern<<<grid, kThreads, smem, st>>>(ta, tw, to, p);
   return check_launch("conv_tc_halo");
 }
 
@@ -372,13 +398,15 @@ int launch_conv_tc_halo(const void* in, const __nv_bfloat16* w, const ConvGeom& 
   p.base_offset_mode = g_halo_boff;
   p.idesc = make_idesc_bf16(128, g.Cout, 0);
   const bool pair = g.Cin == 32;
-  CUtensorMap ta, tw;
+  const bool comp = g.up_cout > 0;
+  const int hw = comp ? 10 : 16;   // composite: tight 10-unit halo pitch frees shared memory for the output staging tiles
+  CUtensorMap ta, tw, to;
   {
     // pair mode: the producer wrote [B][H/2][W][2][32], i.e. an ordinary NHWC tensor of H/2 x W units with 64 "channels"
     const uint64_t uh = pair ? (uint64_t)g.H / 2 : (uint64_t)g.H;
     const uint64_t dims[4] = {64, (uint64_t)g.W, uh, (uint64_t)g.B};
     const uint64_t str[4] = {2, 128, (uint64_t)g.W * 128, uh * g.W * 128};
-    const uint32_t box[4] = {64, kHaloW, kHaloH, 1};
+    const uint32_t box[4] = {64, (uint32_t)hw, kHaloH, 1};
     L2I_TRY(make_tmap(&ta, in, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
   }
   if (g.up_cout > 0) {  // composite up-conv: a plain 3x3 conv at input resolution with N = 4 * Cout
@@ -410,15 +438,26 @@ int launch_conv_tc_halo(const void* in, const __nv_bfloat16* w, const ConvGeom& 
     const uint32_t box[3] = {64, (uint32_t)g.Cout, 1};
     L2I_TRY(make_tmap(&tw, w, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
   }
+  to = ta;
+  p.tma_store = 0;
+  if (comp && !g.out_pair_packed && e.y_out == nullptr && e.out != nullptr && (uintptr_t)e.out % 16 == 0) {
+    // output NHWC [B][2H][2W][32] bf16; a warp's 4 x 8 input pixels of one phase = every other pixel of 4 x 8 output positions
+    const uint64_t dims[4] = {32, (uint64_t)g.out_W, (uint64_t)g.out_H, (uint64_t)g.B};
+    const uint64_t str[4] = {2, 64, (uint64_t)g.out_W * 64, (uint64_t)g.out_H * g.out_W * 64};
+    const uint32_t box[4] = {32, 16, 8, 1};
+    const uint32_t estr[4] = {1, 2, 2, 1};
+    L2I_TRY(make_tmap_strided(&to, e.out, 4, dims, str, box, estr, CU_TENSOR_MAP_SWIZZLE_64B));
+    p.tma_store = 1;
+  }
   p.tiles_x = ceil_div(p.OUW, kTileW); p.tiles_y = ceil_div(p.OUH, kTileH);
   const int64_t total = (int64_t)p.tiles_x * p.tiles_y * g.B;
   if (total <= 0 || total > 0x7fffffff) { set_error("conv_tc_halo: bad tile count"); return L2I_ERR_INVALID_ARG; }
   p.total_tiles = (int)total;
-  if (g.up_cout > 0) return launch_halo_variant<128, 2, 1, false, true, EPI_ACT>(ta, tw, p, st);
-  if (g.nphase == 4) return launch_halo_variant<32, 4, 4, false, false, EPI_RAW>(ta, tw, p, st);
-  if (pair) return launch_halo_variant<32, 4, 2, true, false, EPI_ACT_RGB>(ta, tw, p, st);
-  if (g.Cout == 64) return launch_halo_variant<64, 3, 1, false, false, EPI_ACT_RGB>(ta, tw, p, st);
-  return launch_halo_variant<32, 4, 1, false, false, EPI_ACT_RGB>(ta, tw, p, st);
+  if (comp) return launch_halo_variant<128, 2, 1, false, true, EPI_ACT, 10, 3>(ta, tw, to, p, st);
+  if (g.nphase == 4) return launch_halo_variant<32, 4, 4, false, false, EPI_RAW, 16, 4>(ta, tw, to, p, st);
+  if (pair) return launch_halo_variant<32, 4, 2, true, false, EPI_ACT_RGB, 16, 4>(ta, tw, to, p, st);
+  if (g.Cout == 64) return launch_halo_variant<64, 3, 1, false, false, EPI_ACT_RGB, 16, 4>(ta, tw, to, p, st);
+  return launch_halo_variant<32, 4, 1, false, false, EPI_ACT_RGB, 16, 4>(ta, tw, to, p, st);
 }
 
 // Pair-packed weight tiles for Cin = 32: dst [12][Cout][64] bf16, tile (parity*2 + r)*3 + kw holds

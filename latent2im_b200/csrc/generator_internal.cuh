@@ -55,6 +55,7 @@ struct StyledConvLayer {
   bool composite = false;            // inference forward of this up layer runs the composite kernel (no t intermediate)
   bool split = false;                // tensor-core path uses hi + lo weights (K doubled) to remove the weight rounding error
   float* w_f32_t = nullptr;          // [9][Cout][Cin] fp32, data-gradient convs (training only)
+  __nv_bfloat16* w_bf16_t = nullptr; // [9][Cin][Cout] bf16: data-gradient conv on the tcgen05 kernel (GEMM N = Cin, K = Cout)
   // training state: saved activation y, saved raw up-conv output t, noise used by the last forward
   void* y_save = nullptr;
   void* t_save = nullptr;

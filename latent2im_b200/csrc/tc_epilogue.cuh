@@ -17,6 +17,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&p);
 }
+// TMA tensor store of a staged shared-memory tile (issued by one lane), bulk-group completion
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(smem_u32(src)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t pack_f16(float a, float b) {
   __half2 p = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&p);
@@ -27,7 +38,7 @@ template <int EPI>
 __device__ __forceinline__ void epilogue_chunk32(const uint32_t (&v)[32], const float* s_d, const float* s_b, const float* s_n,
                                                  const float* s_w0, const float* s_w1, const float* s_w2, float nz,
                                                  bool raw_fp16, float& rgb0, float& rgb1, float& rgb2,
-                                                 __nv_bfloat16* __restrict__ outc, __nv_bfloat16* __restrict__ yc) {
+                                                 __nv_bfloat16* __restrict__ outc, __nv_bfloat16* __restrict__ yc, int out_swz = 0) {
   uint32_t packed[16];
   if (EPI == EPI_RAW) {
 #pragma unroll
@@ -73,10 +84,10 @@ __device__ __forceinline__ void epilogue_chunk32(const uint32_t (&v)[32], const 
       for (int k = 0; k < 4; ++k) dst[k] = make_uint4(ypacked[4 * k], ypacked[4 * k + 1], ypacked[4 * k + 2], ypacked[4 * k + 3]);
     }
   }
-  if (outc != nullptr) {
+  if (outc != nullptr) {   // out_swz != 0: outc is this lane's 64-byte slot of a SWIZZLE_64B staging tile (TMA store source)
     uint4* dst = reinterpret_cast<uint4*>(outc);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) dst[k] = make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
+    for (int k = 0; k < 4; ++k) dst[k ^ out_swz] = make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
   }
 }
 

@@ -116,6 +116,9 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int b_is_fp
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
 int make_tmap(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
               const uint32_t* box, CUtensorMapSwizzle swz);
+// bf16 tensor with per-dimension traversal strides (elementStrides), e.g. every other pixel of an image
+int make_tmap_strided(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, const uint32_t* elem_strides, CUtensorMapSwizzle swz);
 // fp32 tensor, no swizzle (epilogue side inputs such as the low-resolution skip image)
 int make_tmap_f32(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box);
