@@ -458,7 +458,8 @@ extern "C" int l2i_generator_set_training(l2i_generator_t* g, int enable) {
     L2I_CUDA_TRY(cudaMemcpy(g->fir2d_dev, k2, sizeof(k2), cudaMemcpyHostToDevice));
     g->train_buffers = true;
   }
-  // data-gradient weight copies follow the current parameters
+  // data-gradient weight copies follow the current parameters (repacked only after a finalize)
+  if (g->train_weights_packed) { g->training = true; return L2I_OK; }
   for (auto& L : g->convs) {
     const float scale = 1.0f / std::sqrt((float)(L.cin * 9));
     const int64_t total = (int64_t)L.cout * L.cin;
@@ -471,6 +472,7 @@ extern "C" int l2i_generator_set_training(l2i_generator_t* g, int enable) {
     }
   }
   L2I_CUDA_TRY(cudaDeviceSynchronize());
+  g->train_weights_packed = true;
   g->training = true;
   return L2I_OK;
 }

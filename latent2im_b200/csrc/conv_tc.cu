@@ -425,7 +425,7 @@ bool conv_tc_supported(const ConvGeom& g, const EpiParams& e) {
   const int bn = pick_block_n(g.Cout);
   if (!(bn == 32 || bn == 64 || bn == 128 || bn == 256)) return false;
   if (g.Cout % bn != 0) return false;
-  if (g.Cin < 64 && bn != 32) return false;  // only the (K=32, N=32) small variant is instantiated
+  if (g.Cin < 64 && bn != 32 && bn != 64) return false;  // K = 32 chunks: N = 32 and N = 64 variants are instantiated
   if (get_encode_fn() == nullptr) return false;
   return true;
 }
@@ -480,6 +480,8 @@ int launch_conv_tc(const void* in, const __nv_bfloat16* w, const ConvGeom& g, co
       case 64: return launch_variant<64, 64, 8, 4>(in, w, p, st);
       case 32: return launch_variant<32, 64, 8, 4>(in, w, p, st);
     }
+  } else if (bn == 64) {
+    return launch_variant<64, 32, 8, 4>(in, w, p, st);
   } else if (bn == 32) {
     return launch_variant<32, 32, 8, 4>(in, w, p, st);
   }

@@ -347,6 +347,7 @@ extern "C" int l2i_generator_finalize(l2i_generator_t* g, void* stream) {
     L2I_TRY(launch_scale_copy(g->mod_b_all + R.s_off, P(g, R.name + ".conv.modulation.bias"), R.cin, 1.f, st));
   }
   g->finalized = true;
+  g->train_weights_packed = false;
   return L2I_OK;
 }
 

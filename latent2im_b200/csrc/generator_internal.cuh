@@ -82,6 +82,7 @@ struct l2i_generator {
   bool finalized = false;
   bool training = false;        // forward keeps what backward needs
   bool train_buffers = false;   // buffers below are allocated
+  bool train_weights_packed = false;  // data-gradient weight copies match the current parameters (reset by finalize)
   int last_batch = 0;
   int last_train_batch = 0;
   void* gbuf = nullptr;         // gradient scratch (activation sized)

@@ -295,6 +295,8 @@ class TransformGraph:
             self.walk = WalkNonLinearW(self.dim_z, self.step, nsliders, self.attrList).to(self.device)
         else:
             raise NotImplementedError("Not implemented latent walk type: {}".format(walk_type))
+        from latent2im_b200 import parallel
+        parallel.broadcast_params(self.walk.parameters(), 0)   # ranks draw different numpy-global inits (transform_base.py:147)
         self.optimizers = torch.optim.Adam(self.walk.parameters(), lr=self.lr, betas=(0.5, 0.99))
 
     # ---- module construction ----------------------------------------------------------------
@@ -373,6 +375,9 @@ class TransformGraph:
         self.optimizers.zero_grad()
         loss = self.get_reg_loss(feed_dict)
         loss.backward()
+        # data parallel (one process per GPU): the only collective of the path, a no-op on a single GPU
+        from latent2im_b200 import parallel
+        parallel.allreduce_mean_grads(self.walk.parameters())
         self.optimizers.step()
         return loss
 
