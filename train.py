@@ -58,7 +58,11 @@ def main(argv=None):
     out_dir = opt.output_dir
     if rank == 0:
         os.makedirs(out_dir, exist_ok=True)
-        logging.basicConfig(filename=os.path.join(out_dir, "log.txt"), filemode="w", level=logging.INFO, format="%(message)s")
+        log = logging.getLogger("latent2im.train")
+        log.setLevel(logging.INFO)
+        for h in list(log.handlers):
+            log.removeHandler(h)
+        log.addHandler(logging.FileHandler(os.path.join(out_dir, "log.txt"), mode="w"))
     b = constants.BATCH_SIZE
     global_b = b * world
     for epoch in range(opt.epochs):
@@ -84,7 +88,7 @@ def main(argv=None):
             loss = g.optimizeParametersAll({"w": w_new, "org": out_zs, "logit": out, "alpha": ag_t}, trainEmbed=opt.trainEmbed,
                                            updateGAN=opt.updateGAN, no_content_loss=opt.no_content_loss, no_gan_loss=opt.no_gan_loss)
             if rank == 0 and i % opt.log_every == 0:
-                logging.info("T, epc, bst, lss, alpha: {}, {}, {}, {}, {}".format(time.time() - t0, epoch, i * global_b,
+                log.info("T, epc, bst, lss, alpha: {}, {}, {}, {}, {}".format(time.time() - t0, epoch, i * global_b,
                                                                                   loss.item(), round(float(at[0]), 2)))
             if rank == 0 and i % opt.model_save_freq == 0:
                 u8 = g.clip_ims(out.detach().float().cpu().numpy()).transpose(0, 2, 3, 1)
@@ -93,6 +97,8 @@ def main(argv=None):
             g.save_multi_models("{}/model_w_{}".format(out_dir, epoch), None)
     if rank == 0:
         g.save_multi_models("{}/model_w_{}_final".format(out_dir, opt.epochs), None)
+        for h in list(log.handlers):
+            h.close()
     if world > 1:
         dist.destroy_process_group()
     return out_dir
