@@ -19,6 +19,7 @@
 // Reference for what is differentiated: networks.py:231-286, 330-358, 460-514; the reference obtains
 // the same gradients from autograd through cuDNN.
 #include <cmath>
+#include <cstdlib>
 #include <type_traits>
 
 #include "generator_internal.cuh"
@@ -370,8 +371,12 @@ int backward_impl(l2i_generator* g, float* grad_latent, const float* grad_image,
       L2I_TRY(launch_act_bwd<T>(g->gbuf, g_xn, nullptr, L.y_save, s_next, g->s_rows, nullptr, 0, nullptr, 0, nullptr, 0, nullptr,
                                 nullptr, g->R_s + L.d_off, nullptr, R_bs, nullptr, 0, B, HWo, L.cout, st));
       const int TH = 2 * L.res_in + 2;
-      L2I_TRY((launch_blur_bwd<T, TIN>(g->tbuf, g->gbuf, L.t_save, demod, g->d_rows, g->R_d + L.d_off, R_bs, B, L.res_out,
-                                       L.res_out, TH, TH, L.cout, g->fir, st)));
+      if (sizeof(T) == 2 && fir_tma_supported(L.cout) && !std::getenv("L2I_FIR_SIMT"))
+        L2I_TRY(launch_blur_bwd_tma(g->tbuf, g->gbuf, L.t_save, demod, g->d_rows, g->R_d + L.d_off, R_bs, B, L.res_out, L.res_out, TH, TH,
+                                    L.cout, g->fir, st));
+      else
+        L2I_TRY((launch_blur_bwd<T, TIN>(g->tbuf, g->gbuf, L.t_save, demod, g->d_rows, g->R_d + L.d_off, R_bs, B, L.res_out,
+                                         L.res_out, TH, TH, L.cout, g->fir, st)));
       geom.H = geom.W = TH; geom.in_scale = 2; geom.taps[0] = dgrad_up_taps();
       L2I_TRY(run_dgrad_conv<T>(g, L, g->tbuf, geom, e, st));
     }

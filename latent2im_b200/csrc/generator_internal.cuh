@@ -23,6 +23,11 @@ int launch_pack_composite_weight(__nv_bfloat16* dst, const float* src, int Cout,
 template <typename T, typename TIN>
 int launch_blur_act(void*, void*, const void*, int, int, int, int, int, int, const float*, int64_t, const float*,
                     const float*, const float*, int64_t, const float*, int, cudaStream_t);
+bool fir_tma_supported(int C);
+int launch_blur_act_tma(void*, void*, const void*, int, int, int, int, int, int, const float*, int64_t, const float*, const float*,
+                        const float*, int64_t, const float*, int, cudaStream_t);
+int launch_blur_bwd_tma(void*, const void*, const void*, const float*, int64_t, float*, int64_t, int, int, int, int, int, int,
+                        const float*, cudaStream_t);
 int launch_skip_combine(float*, const float*, int, const float*, const float*, int, int, int, const float*, cudaStream_t);
 template <typename T> int launch_const_input(void*, const float*, const float*, int64_t, int, int, int, cudaStream_t);
 int launch_demod(float*, int64_t, const float*, int64_t, const float*, const int64_t*, const int*, const int*, int, int, cudaStream_t);
