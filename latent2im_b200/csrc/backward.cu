@@ -34,7 +34,7 @@ struct alignas(sizeof(T) * VEC) GVec { T v[VEC]; };
 // grid = (pixel chunks, B), 256 threads: thread = (pixel slot, 16-byte channel vector).
 // ------------------------------------------------------------------------------------------------
 template <typename T, int VEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 act_bwd_kernel(T* __restrict__ g_out, const T* __restrict__ g_xn, const float* __restrict__ g_rgb,
                const T* __restrict__ y, const float* __restrict__ s_next, int64_t s_next_bs,
                const float* __restrict__ wr, int64_t wr_bs, const float* __restrict__ demod, int64_t demod_bs,
@@ -43,58 +43,76 @@ act_bwd_kernel(T* __restrict__ g_out, const T* __restrict__ g_xn, const float* _
                float* __restrict__ R_rgb, int64_t R_rgb_bs, int HW, int C, int chunk) {
   using V = GVec<T, VEC>;
   constexpr float kSqrt2 = 1.4142135623730951f;
-  extern __shared__ float red[];  // [5][C]
+  // [5][C] block reductions followed by the [6][C] per-channel constants (kept out of registers: the kernel is
+  // latency-bound, two resident CTAs per SM matter more than saving the broadcast LDS)
+  extern __shared__ float red[];
+  float* prm = red + 5 * C;
+  float *p_sn = prm, *p_dm = prm + C, *p_bs = prm + 2 * C, *p_w0 = prm + 3 * C, *p_w1 = prm + 4 * C, *p_w2 = prm + 5 * C;
   const int CV = C / VEC;
   const int slots = 256 / CV;
   const int cv = threadIdx.x % CV, slot = threadIdx.x / CV;
   const int b = blockIdx.y;
   const int c = cv * VEC;
   for (int i = threadIdx.x; i < 5 * C; i += 256) red[i] = 0.f;
-  __syncthreads();
-  float sn[VEC], dm[VEC], bs[VEC], w0[VEC], w1[VEC], w2[VEC];
-#pragma unroll
-  for (int k = 0; k < VEC; ++k) {
-    sn[k] = s_next ? s_next[(int64_t)b * s_next_bs + c + k] : 0.f;
-    dm[k] = demod ? demod[(int64_t)b * demod_bs + c + k] : 1.f;
-    bs[k] = bias ? bias[c + k] : 0.f;
-    w0[k] = wr ? wr[(int64_t)b * wr_bs + c + k] : 0.f;
-    w1[k] = wr ? wr[(int64_t)b * wr_bs + C + c + k] : 0.f;
-    w2[k] = wr ? wr[(int64_t)b * wr_bs + 2 * C + c + k] : 0.f;
+  for (int i = threadIdx.x; i < C; i += 256) {
+    p_sn[i] = s_next ? s_next[(int64_t)b * s_next_bs + i] : 0.f;
+    p_dm[i] = demod ? demod[(int64_t)b * demod_bs + i] : 1.f;
+    p_bs[i] = bias ? bias[i] : 0.f;
+    p_w0[i] = wr ? wr[(int64_t)b * wr_bs + i] : 0.f;
+    p_w1[i] = wr ? wr[(int64_t)b * wr_bs + C + i] : 0.f;
+    p_w2[i] = wr ? wr[(int64_t)b * wr_bs + 2 * C + i] : 0.f;
   }
+  __syncthreads();
   const float nw = (noise != nullptr && noise_w != nullptr) ? *noise_w : 0.f;
   float rs[VEC], rd[VEC], r0[VEC], r1[VEC], r2[VEC];
 #pragma unroll
   for (int k = 0; k < VEC; ++k) rs[k] = rd[k] = r0[k] = r1[k] = r2[k] = 0.f;
   const int p0 = blockIdx.x * chunk, p1 = min(p0 + chunk, HW);
   if (slot < slots) {
-    for (int p = p0 + slot; p < p1; p += slots) {
-      const int64_t off = ((int64_t)b * HW + p) * C + c;
-      const V yv = *reinterpret_cast<const V*>(y + off);
-      V gx;
-      if (g_xn != nullptr) gx = *reinterpret_cast<const V*>(g_xn + off);
-      float gr0 = 0.f, gr1 = 0.f, gr2 = 0.f;
-      if (g_rgb != nullptr) {
-        gr0 = g_rgb[((int64_t)b * 3 + 0) * HW + p];
-        gr1 = g_rgb[((int64_t)b * 3 + 1) * HW + p];
-        gr2 = g_rgb[((int64_t)b * 3 + 2) * HW + p];
-      }
-      const float nz = noise != nullptr ? nw * noise[(int64_t)b * noise_bs + p] : 0.f;
-      V go;
+    constexpr int U = 4;   // pixels in flight per thread: every load of the batch is issued before the first use
+    for (int pb = p0 + slot; pb < p1; pb += U * slots) {
+      V yv[U], gx[U];
+      float gr[U][3], nzv[U];
+      bool ok[U];
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) {
-        const float yk = to_f32<T>(yv.v[k]);
-        const float gxk = g_xn != nullptr ? to_f32<T>(gx.v[k]) : 0.f;
-        const float gy = sn[k] * gxk + w0[k] * gr0 + w1[k] * gr1 + w2[k] * gr2;
-        const float gv = gy * (yk > 0.f ? kSqrt2 : 0.2f * kSqrt2);
-        const float v = yk > 0.f ? yk * (1.f / kSqrt2) : yk * (1.f / (0.2f * kSqrt2));
-        rd[k] = fmaf(gv, v - nz - bs[k], rd[k]);
-        rs[k] = fmaf(gxk, yk, rs[k]);
-        r0[k] = fmaf(gr0, yk, r0[k]);
-        r1[k] = fmaf(gr1, yk, r1[k]);
-        r2[k] = fmaf(gr2, yk, r2[k]);
-        go.v[k] = from_f32<T>(dm[k] * gv);
+      for (int u = 0; u < U; ++u) {
+        const int p = pb + u * slots;
+        ok[u] = p < p1;
+        const int pc = ok[u] ? p : p0;
+        const int64_t off = ((int64_t)b * HW + pc) * C + c;
+        yv[u] = *reinterpret_cast<const V*>(y + off);
+        if (g_xn != nullptr) gx[u] = *reinterpret_cast<const V*>(g_xn + off);
+        gr[u][0] = gr[u][1] = gr[u][2] = 0.f;
+        if (g_rgb != nullptr) {
+          gr[u][0] = g_rgb[((int64_t)b * 3 + 0) * HW + pc];
+          gr[u][1] = g_rgb[((int64_t)b * 3 + 1) * HW + pc];
+          gr[u][2] = g_rgb[((int64_t)b * 3 + 2) * HW + pc];
+        }
+        nzv[u] = noise != nullptr ? nw * noise[(int64_t)b * noise_bs + pc] : 0.f;
       }
-      *reinterpret_cast<V*>(g_out + off) = go;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!ok[u]) continue;
+        const int p = pb + u * slots;
+        const int64_t off = ((int64_t)b * HW + p) * C + c;
+        const float gr0 = gr[u][0], gr1 = gr[u][1], gr2 = gr[u][2], nz = nzv[u];
+        V go;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          const float yk = to_f32<T>(yv[u].v[k]);
+          const float gxk = g_xn != nullptr ? to_f32<T>(gx[u].v[k]) : 0.f;
+          const float gy = p_sn[c + k] * gxk + p_w0[c + k] * gr0 + p_w1[c + k] * gr1 + p_w2[c + k] * gr2;
+          const float gv = gy * (yk > 0.f ? kSqrt2 : 0.2f * kSqrt2);
+          const float v = yk > 0.f ? yk * (1.f / kSqrt2) : yk * (1.f / (0.2f * kSqrt2));
+          rd[k] = fmaf(gv, v - nz - p_bs[c + k], rd[k]);
+          rs[k] = fmaf(gxk, yk, rs[k]);
+          r0[k] = fmaf(gr0, yk, r0[k]);
+          r1[k] = fmaf(gr1, yk, r1[k]);
+          r2[k] = fmaf(gr2, yk, r2[k]);
+          go.v[k] = from_f32<T>(p_dm[c + k] * gv);
+        }
+        *reinterpret_cast<V*>(g_out + off) = go;
+      }
     }
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
@@ -272,11 +290,11 @@ int launch_act_bwd(void* g_out, const void* g_xn, const float* g_rgb, const void
                    const float* wr, int64_t wr_bs, const float* demod, int64_t demod_bs, const float* noise, int64_t noise_bs,
                    const float* noise_w, const float* bias, float* R_s, float* R_d, int64_t R_bs, float* R_rgb,
                    int64_t R_rgb_bs, int B, int HW, int C, cudaStream_t st) {
-  constexpr int VEC = 16 / sizeof(T);
+  constexpr int VEC = 4;   // 8-byte (bf16) / 16-byte (fp32) vectors: small register arrays leave room for 4 pixels in flight
   if (C % VEC != 0 || C / VEC > 256) { set_error("act_bwd: unsupported C=%d", C); return L2I_ERR_UNSUPPORTED; }
   const int chunk = std::max(256, std::min(HW, 4096));
   dim3 grid(ceil_div(HW, chunk), B);
-  act_bwd_kernel<T, VEC><<<grid, 256, sizeof(float) * 5 * C, st>>>(
+  act_bwd_kernel<T, VEC><<<grid, 256, sizeof(float) * 11 * C, st>>>(
       (T*)g_out, (const T*)g_xn, g_rgb, (const T*)y, s_next, s_next_bs, wr, wr_bs, demod, demod_bs, noise, noise_bs, noise_w,
       bias, R_s, R_d, R_bs, R_rgb, R_rgb_bs, HW, C, chunk);
   return check_launch("act_bwd");
