@@ -96,7 +96,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // A halo stages, then the resident weights
   uint8_t* smem_w = smem + STAGES * kStageBytes;
   const int wbytes = p.nwtiles * kWTileBytes;
-  uint8_t* smem_stage_out = smem_w + ((wbytes + 1023) & ~1023);   // composite + tma_store: 2 KB per epilogue warp
+  constexpr int kStageOutBytes = COMP ? 2048 : 32 * N * 2;         // per epilogue warp: 32 pixels x one output row (64 B / 2N B)
+  uint8_t* smem_stage_out = smem_w + ((wbytes + 1023) & ~1023);   // tma_store: swizzled output staging tiles
   __shared__ __align__(16) float epi_smem[kGroups * kEpiFloats];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
@@ -109,7 +110,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_w);
-    if (COMP && p.tma_store) prefetch_tmap(&tmap_o);
+    if (p.tma_store) prefetch_tmap(&tmap_o);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -200,9 +201,12 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int64_t plane = (int64_t)p.out_H * p.out_W;
     const int lx = row & 7, ly = row >> 3;
     const bool raw_fp16 = e.raw_fp16 != 0;
-    const bool use_tma_store = COMP && p.tma_store != 0;
-    __nv_bfloat16* stage_out = (__nv_bfloat16*)(smem_stage_out + (warp - 4) * 2048) + lane * 32;   // this lane's 64-byte slot
-    const int stage_swz = (lane >> 1) & 3;                                                       // SWIZZLE_64B: chunk ^= address bits [7:8]
+    const bool use_tma_store = p.tma_store != 0;
+    uint8_t* stage_tile = smem_stage_out + (warp - 4) * kStageOutBytes;
+    // this lane's row of the staging tile: 64 B rows under SWIZZLE_64B (chunk ^= address bits [7:8]) for the composite
+    // kernel, 2N-byte (128 B) rows under SWIZZLE_128B (chunk ^= row & 7) for the plain one
+    __nv_bfloat16* stage_out = (__nv_bfloat16*)stage_tile + lane * (COMP ? 32 : N);
+    const int stage_swz = COMP ? ((lane >> 1) & 3) : (lane & 7);
     uint32_t grp_phase = 0;
     int staged_b = -1;
     int it = 0;
@@ -299,7 +303,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               fence_proxy_async_smem();
               __syncwarp();
               if (lane == 0)
-                tma_store_4d(&tmap_o, smem_stage_out + (warp - 4) * 2048, 0, 2 * x0 + (phc & 1), 2 * (y0 + 4 * q) + (phc >> 1), b);
+                tma_store_4d(&tmap_o, stage_tile, 0, 2 * x0 + (phc & 1), 2 * (y0 + 4 * q) + (phc >> 1), b);
               continue;
             }
             if (ok[a]) {
@@ -309,6 +313,22 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               if (e.out != nullptr) outc = (__nv_bfloat16*)e.out + opix * CO;
               if (e.y_out != nullptr) yc = (__nv_bfloat16*)e.y_out + pixc * CO;
             }
+          }
+          if (!COMP && use_tma_store) {
+            // plain N = 64 layer: the warp's 4 x 8 pixels x 128 B go through a SWIZZLE_128B staging tile and one TMA store
+            if (c0 == 0) {
+              if (lane == 0) tma_store_wait_read();
+              __syncwarp();
+            }
+            tmem_ld_wait();
+            epilogue_chunk32<EPI>(v, s_d + cs, s_b + cs, s_n + cs, s_w + cs, s_w + CO + cs, s_w + 2 * CO + cs, nzc, raw_fp16,
+                                  rgb0, rgb1, rgb2, stage_out, nullptr, stage_swz, c0 >> 3);
+            if (c0 + 32 >= N) {
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) tma_store_4d(&tmap_o, stage_tile, 0, x0, y0 + 4 * q, b);
+            }
+            continue;
           }
           tmem_ld_wait();
           epilogue_chunk32<EPI>(v, s_d + cs, s_b + cs, s_n + cs, s_w + cs, s_w + CO + cs, s_w + 2 * CO + cs, nzc, raw_fp16,
@@ -331,7 +351,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   }
 
-  if (COMP && p.tma_store && warp >= 4 && lane == 0) tma_store_wait_all();   // outstanding bulk stores must land before exit
+  if (p.tma_store && warp >= 4 && lane == 0) tma_store_wait_all();   // outstanding bulk stores must land before exit
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -344,7 +364,7 @@ template <int N, int STAGES, int NACC, bool PAIR, bool COMP, int EPI, int HW, in
 int launch_halo_variant(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const HaloParams& p, cudaStream_t st) {
   const int wbytes = (p.nwtiles * N * 128 + 1023) & ~1023;
   // + alignment slack; epilogue vectors and barriers are static; composite: 2 KB output staging tile per epilogue warp
-  const int smem = STAGES * halo_stage_bytes(HW) + wbytes + 1024 + (COMP ? kGroups * 4 * 2048 : 0);
+  const int smem = STAGES * halo_stage_bytes(HW) + wbytes + 1024 + (p.tma_store ? kGroups * 4 * (COMP ? 2048 : 32 * N * 2) : 0);
   constexpr int kThreads = 128 + kGroups * 128;
   if (smem > 227 * 1024) {
     set_error("conv_tc_halo: shared memory budget exceeded (%d bytes)", smem);
@@ -399,7 +419,10 @@ int launch_conv_tc_halo(const void* in, const __nv_bfloat16* w, const ConvGeom& 
   p.idesc = make_idesc_bf16(128, g.Cout, 0);
   const bool pair = g.Cin == 32;
   const bool comp = g.up_cout > 0;
-  const int hw = comp ? 10 : 16;   // composite: tight 10-unit halo pitch frees shared memory for the output staging tiles
+  // plain 64 -> 64 layer whose activation output goes through TMA stores (inference: no y_out, single sample layout)
+  const bool plain64 = !comp && !pair && g.nphase == 1 && g.Cout == 64 && e.mode == 0 && e.out != nullptr && e.s_next != nullptr &&
+                       e.y_out == nullptr && (uintptr_t)e.out % 16 == 0 && (g.OW % 8 == 0) && (g.OH % 4 == 0);
+  const int hw = (comp || plain64) ? 10 : 16;   // tight 10-unit halo pitch frees shared memory for the output staging tiles
   CUtensorMap ta, tw, to;
   {
     // pair mode: the producer wrote [B][H/2][W][2][32], i.e. an ordinary NHWC tensor of H/2 x W units with 64 "channels"
@@ -449,6 +472,13 @@ int launch_conv_tc_halo(const void* in, const __nv_bfloat16* w, const ConvGeom& 
     L2I_TRY(make_tmap_strided(&to, e.out, 4, dims, str, box, estr, CU_TENSOR_MAP_SWIZZLE_64B));
     p.tma_store = 1;
   }
+  if (plain64) {
+    const uint64_t dims[4] = {64, (uint64_t)g.out_W, (uint64_t)g.out_H, (uint64_t)g.B};
+    const uint64_t str[4] = {2, 128, (uint64_t)g.out_W * 128, (uint64_t)g.out_H * g.out_W * 128};
+    const uint32_t box[4] = {64, 8, 4, 1};
+    L2I_TRY(make_tmap(&to, e.out, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+    p.tma_store = 1;
+  }
   p.tiles_x = ceil_div(p.OUW, kTileW); p.tiles_y = ceil_div(p.OUH, kTileH);
   const int64_t total = (int64_t)p.tiles_x * p.tiles_y * g.B;
   if (total <= 0 || total > 0x7fffffff) { set_error("conv_tc_halo: bad tile count"); return L2I_ERR_INVALID_ARG; }
@@ -456,6 +486,7 @@ int launch_conv_tc_halo(const void* in, const __nv_bfloat16* w, const ConvGeom& 
   if (comp) return launch_halo_variant<128, 2, 1, false, true, EPI_ACT, 10, 3>(ta, tw, to, p, st);
   if (g.nphase == 4) return launch_halo_variant<32, 4, 4, false, false, EPI_RAW, 16, 4>(ta, tw, to, p, st);
   if (pair) return launch_halo_variant<32, 4, 2, true, false, EPI_ACT_RGB, 16, 4>(ta, tw, to, p, st);
+  if (plain64) return launch_halo_variant<64, 3, 1, false, false, EPI_ACT_RGB, 10, 4>(ta, tw, to, p, st);
   if (g.Cout == 64) return launch_halo_variant<64, 3, 1, false, false, EPI_ACT_RGB, 16, 4>(ta, tw, to, p, st);
   return launch_halo_variant<32, 4, 1, false, false, EPI_ACT_RGB, 16, 4>(ta, tw, to, p, st);
 }

@@ -38,7 +38,7 @@ template <int EPI>
 __device__ __forceinline__ void epilogue_chunk32(const uint32_t (&v)[32], const float* s_d, const float* s_b, const float* s_n,
                                                  const float* s_w0, const float* s_w1, const float* s_w2, float nz,
                                                  bool raw_fp16, float& rgb0, float& rgb1, float& rgb2,
-                                                 __nv_bfloat16* __restrict__ outc, __nv_bfloat16* __restrict__ yc, int out_swz = 0) {
+                                                 __nv_bfloat16* __restrict__ outc, __nv_bfloat16* __restrict__ yc, int out_swz = 0, int piece_base = 0) {
   uint32_t packed[16];
   if (EPI == EPI_RAW) {
 #pragma unroll
@@ -84,10 +84,10 @@ __device__ __forceinline__ void epilogue_chunk32(const uint32_t (&v)[32], const 
       for (int k = 0; k < 4; ++k) dst[k] = make_uint4(ypacked[4 * k], ypacked[4 * k + 1], ypacked[4 * k + 2], ypacked[4 * k + 3]);
     }
   }
-  if (outc != nullptr) {   // out_swz != 0: outc is this lane's 64-byte slot of a SWIZZLE_64B staging tile (TMA store source)
+  if (outc != nullptr) {   // staging mode (TMA store source): outc = this lane's row of a swizzled tile, 16-byte piece (piece_base + k) ^ out_swz
     uint4* dst = reinterpret_cast<uint4*>(outc);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) dst[k ^ out_swz] = make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
+    for (int k = 0; k < 4; ++k) dst[(piece_base + k) ^ out_swz] = make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
   }
 }
 
