@@ -283,6 +283,16 @@ extern "C" int l2i_generator_create(l2i_generator_t** out, int size, int style_d
   if (rc == L2I_OK) rc = dev_alloc(g, &g->map_buf[0], B * (int64_t)D);
   if (rc == L2I_OK) rc = dev_alloc(g, &g->map_buf[1], B * (int64_t)D);
   if (rc != L2I_OK) return fail(rc);
+  if (n_mlp > 0) {
+    rc = dev_alloc(g, &g->map_w_ptrs, n_mlp);
+    if (rc == L2I_OK) rc = dev_alloc(g, &g->map_b_ptrs, n_mlp);
+    if (rc != L2I_OK) return fail(rc);
+    std::vector<const float*> wp(n_mlp), bp(n_mlp);
+    for (int i = 1; i <= n_mlp; ++i) { wp[i - 1] = P(g, "style." + std::to_string(i) + ".weight"); bp[i - 1] = P(g, "style." + std::to_string(i) + ".bias"); }
+    cudaError_t e = cudaMemcpy(g->map_w_ptrs, wp.data(), sizeof(float*) * n_mlp, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(g->map_b_ptrs, bp.data(), sizeof(float*) * n_mlp, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { set_error("generator_create: mapping table upload failed: %s", cudaGetErrorString(e)); return fail(L2I_ERR_CUDA); }
+  }
   g->conv_out.assign(g->convs.size(), nullptr);
   g->skip_out.assign(g->rgbs.size(), nullptr);
   *out = g;
@@ -358,6 +368,10 @@ extern "C" int l2i_generator_mapping(l2i_generator_t* g, float* w, const float* 
   if (batch == 0) return L2I_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int D = g->D;
+  if (g->n_mlp > 0 && D % 4 == 0 && D <= 4096) {   // PixelNorm + every mapping layer in one launch
+    const float ws = (1.0f / std::sqrt((float)D)) * g->lr_mlp;
+    return launch_mapping_fused(w, z, g->map_w_ptrs, g->map_b_ptrs, batch, g->n_mlp, D, ws, g->lr_mlp, st);
+  }
   float* cur = g->n_mlp == 0 ? w : g->map_buf[0];
   L2I_TRY(l2i_pixel_norm(cur, z, batch, D, stream));
   const float wscale = (1.0f / std::sqrt((float)D)) * g->lr_mlp;

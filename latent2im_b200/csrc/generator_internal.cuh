@@ -36,6 +36,7 @@ int launch_gather_latent(float*, const float*, int64_t, int64_t, int, int, int, 
 int launch_pack_conv_weight(float*, __nv_bfloat16*, float*, const float*, int, int, int, float, int, cudaStream_t);
 int launch_scale_copy(float*, const float*, int64_t, float, cudaStream_t);
 template <typename T> int launch_nhwc_to_nchw(float*, const void*, int, int, int, int, const float*, int64_t, cudaStream_t);
+int launch_mapping_fused(float*, const float*, const float* const*, const float* const*, int, int, int, float, float, cudaStream_t);
 int launch_linear(float*, int64_t, const float*, int64_t, const int*, const float*, const float*, int, int, int,
                   float, float, int, float, float, cudaStream_t);
 
@@ -121,6 +122,8 @@ struct l2i_generator {
   float* rgb_part = nullptr;
   float* skip[2] = {nullptr, nullptr};
   float* map_buf[2] = {nullptr, nullptr};
+  const float** map_w_ptrs = nullptr;   // device tables of the mapping layers' weight / bias pointers (fused mapping kernel)
+  const float** map_b_ptrs = nullptr;
   // where each layer's output landed in the last forward (debug taps)
   std::vector<const void*> conv_out;
   std::vector<const float*> skip_out;

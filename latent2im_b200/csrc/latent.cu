@@ -57,6 +57,70 @@ int launch_linear(float* y, int64_t y_stride, const float* x, int64_t x_stride, 
   return check_launch("linear");
 }
 
+// Whole mapping network in one launch (Generator.style, networks.py:374-382): PixelNorm, then n_mlp x
+// [EqualLinear(D, D, lr_mul) + fused leaky relu].  One CTA per latent row keeps the activation vector in shared
+// memory between layers, so the 8 dependent layers cost one launch instead of 9; every warp produces D/16 outputs per
+// layer, four weight rows (16 independent 16-byte loads per lane) in flight at a time.  Weights stream from L2.
+constexpr int kMapThreads = 512;
+__global__ void __launch_bounds__(kMapThreads)
+mapping_fused_kernel(float* __restrict__ w_out, const float* __restrict__ z, const float* const* __restrict__ Ws,
+                     const float* const* __restrict__ bs, int n_mlp, int D, float wscale, float bscale) {
+  extern __shared__ float xbuf[];   // [2][D]
+  __shared__ float red[kMapThreads / 32];
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kWarps = kMapThreads / 32;
+  // PixelNorm (networks.py:11-16)
+  float ss = 0.f;
+  for (int k = threadIdx.x; k < D; k += kMapThreads) { const float v = z[(int64_t)b * D + k]; xbuf[k] = v; ss = fmaf(v, v, ss); }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+  if (lane == 0) red[warp] = ss;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < kWarps; ++i) tot += red[i];
+  const float rn = rsqrtf(tot / (float)D + 1e-8f);
+  for (int k = threadIdx.x; k < D; k += kMapThreads) xbuf[k] *= rn;
+  __syncthreads();
+  float* cur = xbuf;
+  float* nxt = xbuf + D;
+  const int D4 = D >> 2;
+  for (int l = 0; l < n_mlp; ++l) {
+    const float* W = Ws[l];
+    const float* bias = bs[l];
+    for (int n0 = warp * 4; n0 < D; n0 += kWarps * 4) {   // 4 output rows per pass (D % 4 == 0)
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int k4 = lane; k4 < D4; k4 += 32) {
+        const float4 xv = *reinterpret_cast<const float4*>(cur + 4 * k4);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float4 wv = __ldg(reinterpret_cast<const float4*>(W + (int64_t)(n0 + r) * D) + k4);
+          acc[r] = fmaf(wv.x, xv.x, fmaf(wv.y, xv.y, fmaf(wv.z, xv.z, fmaf(wv.w, xv.w, acc[r]))));
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        float v = acc[r];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) {
+          v = v * wscale + bias[n0 + r] * bscale;
+          nxt[n0 + r] = lrelu(v, 0.2f) * 1.4142135623730951f;
+        }
+      }
+    }
+    __syncthreads();
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  for (int k = threadIdx.x; k < D; k += kMapThreads) w_out[(int64_t)b * D + k] = cur[k];
+}
+
+int launch_mapping_fused(float* w, const float* z, const float* const* Ws, const float* const* bs, int B, int n_mlp, int D,
+                         float wscale, float bscale, cudaStream_t st) {
+  if (B == 0) return L2I_OK;
+  mapping_fused_kernel<<<B, kMapThreads, sizeof(float) * 2 * D, st>>>(w, z, Ws, bs, n_mlp, D, wscale, bscale);
+  return check_launch("mapping_fused");
+}
+
 __global__ void __launch_bounds__(128) pixel_norm_kernel(float* __restrict__ y, const float* __restrict__ x,
                                                          int B, int D) {
   const int b = blockIdx.x;

@@ -46,7 +46,7 @@ def test_fp32_intermediates_and_skips():
     lat = _latent(spec, 2)
     noise = synthetic_noise(spec.num_layers, 2)
     ref, inter = generator_forward_ref(sd, lat.double(), noise, spec, return_intermediates=True)
-    gen(lat.cuda(), input_is_latent=True, noise=[n.cuda() for n in noise])
+    img, _ = gen(lat.cuda(), input_is_latent=True, noise=[n.cuda() for n in noise])  # keep it: the last skip IS this tensor
     last = f"convs.{spec.num_layers - 3}"  # the newest materialised activation (ping-pong buffers)
     got = gen.read_activation(last).cpu().double()
     assert (got - inter[last]).abs().max() <= 1e-3
