@@ -1,0 +1,337 @@
+// A-resident / B-streamed tcgen05 implicit-GEMM conv for the Cin = 128 layers (256 x 256 px, plain 128 -> 128 with the
+// act + ToRGB epilogue, and the composite 128 -> 4 x 64 up-conv).
+//
+// The general kernel (conv_tc.cu) reloads the activation tile for every tap: 9 x 16 KB of A plus 9 x 16/32 KB of B per
+// 128-pixel tile and 64-channel chunk.  With N <= 256 and K = 128 per tap its MMAs are short, so that traffic (and the
+// depth of the TMA ring needed to cover its latency) bounds the layer (ncu: tensor pipe 47 % / 65 % active).  Here the
+// (8+2) x (16+2) pixel halo tile of the activation (two 64-channel planes, 46 KB) is TMA-loaded ONCE per output tile and
+// the nine taps are UMMA descriptors at tap-shifted start addresses (as in conv_tc_halo.cu); only the weight tiles
+// stream through a shared-memory ring, fed by their own producer warp.  L2 -> SMEM bytes per tile: 46 KB + 9 x 2 x B-tile
+// instead of 9 x 2 x (16 KB + B-tile).
+#include "tc_epilogue.cuh"
+
+namespace l2i {
+
+using namespace tc;
+
+namespace {
+
+constexpr int kRW = 10, kRH = 18;                          // halo tile (pixels): 8 + 2 wide, 16 + 2 tall
+constexpr int kRPlaneBytes = kRW * kRH * 128;              // 23040: one 64-channel plane
+constexpr int kRPlaneStride = (kRPlaneBytes + 1023) & ~1023;
+constexpr int kRAStages = 2;
+constexpr int kRTileW = 8, kRTileH = 16;
+
+struct AresParams {
+  int B, H, W;               // input = output grid of the GEMM rows
+  int Cout;                  // real output channels (N for the plain layer, N / 4 for the composite up-conv)
+  int out_H, out_W;
+  int tiles_x, tiles_y, total_tiles;
+  uint32_t idesc;
+  EpiParams e;
+};
+
+__device__ __forceinline__ uint64_t ares_desc(uint32_t addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void ares_group_sync(int group) {
+  asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+}
+
+// N = GEMM N, KC = 64-channel chunks of Cin, BP = chunks per weight-ring stage (1 or KC), WST = weight ring stages,
+// COMP = composite up-conv (N = 4 phases x N/4).  The single MMA-issuing thread pays ~100 clocks of mbarrier latency per
+// ring stage; with N = 128 a 64-channel stage is only 256 tensor clocks, so those layers take whole taps (BP = KC) per stage.
+template <int N, int KC, int BP, int WST, int GROUPS, int EPI, bool COMP>
+__global__ void __launch_bounds__(128 + GROUPS * 128, 1)
+conv_tc_ares_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                    const __grid_constant__ AresParams p) {
+  constexpr int kAStageBytes = KC * kRPlaneStride;
+  constexpr int kBPlaneBytes = N * 128;
+  constexpr int kBStageBytes = BP * kBPlaneBytes;
+  static_assert(KC % BP == 0, "ring stage = BP chunks of one tap");
+  constexpr int CO = COMP ? N / 4 : N;
+  constexpr int kEpiFloats = 6 * CO;
+  static_assert(GROUPS * N <= 512, "TMEM budget");
+  static_assert(!COMP || EPI == EPI_ACT, "composite variant uses the act-only epilogue");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem_b = smem + kRAStages * kAStageBytes;
+  __shared__ __align__(16) float epi_smem[GROUPS * kEpiFloats];
+  __shared__ __align__(8) uint64_t a_full[kRAStages];
+  __shared__ __align__(8) uint64_t a_empty[kRAStages];
+  __shared__ __align__(8) uint64_t w_full[WST];
+  __shared__ __align__(8) uint64_t w_empty[WST];
+  __shared__ __align__(8) uint64_t tmem_full[GROUPS];
+  __shared__ __align__(8) uint64_t tmem_empty[GROUPS];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kRAStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < WST; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int a = 0; a < GROUPS; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  auto decode = [&](int tile, int& x0, int& y0, int& b) {
+    const int tx = tile % p.tiles_x;
+    const int r = tile / p.tiles_x;
+    const int ty = r % p.tiles_y;
+    b = r / p.tiles_y;
+    x0 = tx * kRTileW; y0 = ty * kRTileH;
+  };
+
+  if (warp == 0) {
+    // ===================== A producer: the halo tile (KC planes) once per output tile =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase_bit = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int x0, y0, b;
+        decode(tile, x0, y0, b);
+        mbar_wait(&a_empty[stage], phase_bit ^ 1);
+        mbar_expect_tx(&a_full[stage], KC * kRPlaneBytes);
+#pragma unroll
+        for (int kc = 0; kc < KC; ++kc)
+          tma_load_4d(smem + stage * kAStageBytes + kc * kRPlaneStride, &tmap_a, &a_full[stage], kc * 64, x0 - 1, y0 - 1, b);
+        if (++stage == kRAStages) { stage = 0; phase_bit ^= 1; }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== B producer: 9 taps x KC weight tiles per output tile through the ring ===========
+    if (lane == 0) {
+      int ws = 0;
+      uint32_t wphase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int t = 0; t < 9; ++t) {
+#pragma unroll
+          for (int kc = 0; kc < KC; kc += BP) {
+            mbar_wait(&w_empty[ws], wphase ^ 1);
+            mbar_expect_tx(&w_full[ws], kBStageBytes);
+#pragma unroll
+            for (int j = 0; j < BP; ++j)
+              tma_load_3d(smem_b + ws * kBStageBytes + j * kBPlaneBytes, &tmap_w, &w_full[ws], (kc + j) * 64, 0, t);
+            if (++ws == WST) { ws = 0; wphase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0, ws = 0, grp = 0;
+      uint32_t phase_bit = 0, wphase = 0, grp_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[grp], grp_phase ^ 1);
+        mbar_wait(&a_full[stage], phase_bit);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smem + stage * kAStageBytes);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(grp * N);
+        for (int t = 0; t < 9; ++t) {
+          const uint32_t shift = (uint32_t)(((t / 3) * kRW + (t % 3)) * 128);   // tap (dy, dx) = (t/3 - 1, t%3 - 1)
+#pragma unroll
+          for (int kc = 0; kc < KC; kc += BP) {
+            mbar_wait(&w_full[ws], wphase);
+            tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < BP; ++j) {
+              const uint32_t a_tap = a_base + (uint32_t)((kc + j) * kRPlaneStride) + shift;
+              const uint32_t b_tile = smem_u32(smem_b + ws * kBStageBytes + j * kBPlaneBytes);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem_d, ares_desc(a_tap + k * 32, kRW * 128), ares_desc(b_tile + k * 32, 1024), p.idesc,
+                          (t | kc | j | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&w_empty[ws]);
+            if (++ws == WST) { ws = 0; wphase ^= 1; }
+          }
+        }
+        umma_commit(&a_empty[stage]);
+        umma_commit(&tmem_full[grp]);
+        if (++stage == kRAStages) { stage = 0; phase_bit ^= 1; }
+        if (++grp == GROUPS) { grp = 0; grp_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const EpiParams& e = p.e;
+    const int group = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int gtid = threadIdx.x - (128 + group * 128);
+    float* sp = epi_smem + group * kEpiFloats;
+    float* s_d = sp;
+    float* s_b = sp + CO;
+    float* s_n = sp + 2 * CO;
+    float* s_w = sp + 3 * CO;
+    constexpr float kSqrt2 = 1.4142135623730951f;
+    const float nw = (e.noise != nullptr && e.noise_w != nullptr) ? __ldg(e.noise_w) * kSqrt2 : 0.f;
+    const int64_t plane = (int64_t)p.out_H * p.out_W;
+    const int lx = row & 7, ly = row >> 3;
+    uint32_t grp_phase = 0;
+    int staged_b = -1;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      if (it % GROUPS != group) continue;
+      int x0, y0, b;
+      decode(tile, x0, y0, b);
+      const int ox = x0 + lx, oy = y0 + ly;
+      const bool ok = ox < p.W && oy < p.H;
+
+      if (b != staged_b) {
+        ares_group_sync(group);
+        for (int j = gtid; j < CO; j += 128) {
+          s_d[j] = (e.demod != nullptr ? __ldg(e.demod + (int64_t)b * e.demod_bs + j) : 1.f) * kSqrt2;
+          s_b[j] = __ldg(e.bias + j) * kSqrt2;
+          s_n[j] = e.s_next ? __ldg(e.s_next + (int64_t)b * e.s_next_bs + j) : 1.f;
+          if (EPI == EPI_ACT_RGB) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) s_w[c * CO + j] = e.wr ? __ldg(e.wr + (int64_t)b * e.wr_bs + c * p.Cout + j) : 0.f;
+          }
+        }
+        ares_group_sync(group);
+        staged_b = b;
+      }
+
+      // ---- global loads of the tile before waiting for the accumulator ----
+      float nzq[4] = {0.f, 0.f, 0.f, 0.f};
+      float up[3] = {0.f, 0.f, 0.f};
+      if (ok && e.noise != nullptr) {
+        if (COMP) {
+          const float* np = e.noise + (int64_t)b * e.noise_bs + (int64_t)(2 * oy) * p.out_W + 2 * ox;
+          const float2 n01 = __ldg(reinterpret_cast<const float2*>(np));
+          const float2 n23 = __ldg(reinterpret_cast<const float2*>(np + p.out_W));
+          nzq[0] = nw * n01.x; nzq[1] = nw * n01.y; nzq[2] = nw * n23.x; nzq[3] = nw * n23.y;
+        } else {
+          nzq[0] = nw * __ldg(e.noise + (int64_t)b * e.noise_bs + (int64_t)oy * p.out_W + ox);
+        }
+      }
+      if (EPI == EPI_ACT_RGB && ok && e.fused_skip) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          up[c] = __ldg(e.rgb_bias + c);
+          if (e.skip_in != nullptr)
+            up[c] += upsample2x_at(e.skip_in + ((int64_t)b * 3 + c) * (plane / 4), p.out_H / 2, p.out_W / 2, oy, ox, e.fir);
+        }
+      }
+
+      mbar_wait(&tmem_full[group], grp_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(group * N);
+      float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        const int phc = COMP ? c0 / CO : 0;            // composite: the chunk's output phase (py*2 + px)
+        const int cs = COMP ? c0 % CO : c0;            // first channel of the chunk
+        const float nzc = phc == 0 ? nzq[0] : (phc == 1 ? nzq[1] : (phc == 2 ? nzq[2] : nzq[3]));
+        __nv_bfloat16* outc = nullptr;
+        __nv_bfloat16* yc = nullptr;
+        if (ok) {
+          const int Y = COMP ? 2 * oy + (phc >> 1) : oy, X = COMP ? 2 * ox + (phc & 1) : ox;
+          const int64_t pix = ((int64_t)b * p.out_H + Y) * p.out_W + X;
+          if (e.out != nullptr && e.s_next != nullptr) outc = (__nv_bfloat16*)e.out + pix * p.Cout + cs;
+          if (e.y_out != nullptr) yc = (__nv_bfloat16*)e.y_out + pix * p.Cout + cs;
+        }
+        tmem_ld_wait();
+        epilogue_chunk32<EPI>(v, s_d + cs, s_b + cs, s_n + cs, s_w + cs, s_w + CO + cs, s_w + 2 * CO + cs, nzc, false, rgb0, rgb1,
+                              rgb2, outc, yc);
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[group]);
+      grp_phase ^= 1;
+
+      if (EPI == EPI_ACT_RGB && e.wr != nullptr && ok) {
+        const float r3[3] = {rgb0, rgb1, rgb2};
+        float* dst = e.fused_skip ? e.skip_out : e.rgb_part;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) dst[((int64_t)b * 3 + c) * plane + (int64_t)oy * p.out_W + ox] = r3[c] + up[c];
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int N, int KC, int BP, int WST, int GROUPS, int EPI, bool COMP>
+int launch_ares_variant(const CUtensorMap& ta, const CUtensorMap& tw, const AresParams& p, cudaStream_t st) {
+  constexpr int smem = kRAStages * KC * kRPlaneStride + WST * BP * N * 128 + 1024;
+  static_assert(smem + GROUPS * 6 * (COMP ? N / 4 : N) * 4 + 512 <= 227 * 1024, "shared memory budget (dynamic + static epilogue vectors)");
+  auto kern = conv_tc_ares_kernel<N, KC, BP, WST, GROUPS, EPI, COMP>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    L2I_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int grid = std::min(p.total_tiles, kNumSMs);
+  kern<<<grid, 128 + GROUPS * 128, smem, st>>>(ta, tw, p);
+  return check_launch("conv_tc_ares");
+}
+
+}  // namespace
+
+bool conv_tc_ares_supported(const ConvGeom& g, const EpiParams& e) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* env = std::getenv("L2I_ARES");
+    enabled = (env != nullptr && env[0] == '0') ? 0 : 1;
+  }
+  if (!enabled || !tmap_available()) return false;
+  if (g.nphase != 1 || g.in_scale != 1 || g.weight_taps != 9 || g.in_pair_packed || g.out_pair_packed) return false;
+  if (g.Cin != 128 || g.H < 16 || g.W < 16 || e.mode != 0) return false;
+  if (g.up_cout > 0) return g.up_cout == 64 && g.Cout == 256 && e.wr == nullptr;
+  return g.Cout == 128 && e.wr != nullptr && e.fused_skip;
+}
+
+// w: [9][N][128] bf16 (plain: N = Cout; composite: N = 4 * Cout rows (phase, co))
+int launch_conv_tc_ares(const void* in, const __nv_bfloat16* w, const ConvGeom& g, const EpiParams& e, cudaStream_t st) {
+  AresParams p{};
+  p.B = g.B; p.H = g.H; p.W = g.W; p.out_H = g.out_H; p.out_W = g.out_W; p.e = e;
+  const bool comp = g.up_cout > 0;
+  p.Cout = comp ? g.up_cout : g.Cout;
+  p.idesc = make_idesc_bf16(128, g.Cout, 0);
+  CUtensorMap ta, tw;
+  {
+    const uint64_t dims[4] = {(uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
+    const uint64_t str[4] = {2, (uint64_t)g.Cin * 2, (uint64_t)g.W * g.Cin * 2, (uint64_t)g.H * g.W * g.Cin * 2};
+    const uint32_t box[4] = {64, kRW, kRH, 1};
+    L2I_TRY(make_tmap(&ta, in, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)g.Cin, (uint64_t)g.Cout, 9};
+    const uint64_t str[3] = {2, (uint64_t)g.Cin * 2, (uint64_t)g.Cout * g.Cin * 2};
+    const uint32_t box[3] = {64, (uint32_t)g.Cout, 1};
+    L2I_TRY(make_tmap(&tw, w, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  p.tiles_x = ceil_div(g.W, kRTileW); p.tiles_y = ceil_div(g.H, kRTileH);
+  const int64_t total = (int64_t)p.tiles_x * p.tiles_y * g.B;
+  if (total <= 0 || total > 0x7fffffff) { set_error("conv_tc_ares: bad tile count"); return L2I_ERR_INVALID_ARG; }
+  p.total_tiles = (int)total;
+  // ring depth: the weight tiles in flight must cover the L2 latency (~1.5-2k clocks): 7 x 256 / 4 x 512 MMA clocks
+  if (comp) return launch_ares_variant<256, 2, 1, 4, 2, EPI_ACT, true>(ta, tw, p, st);
+  return launch_ares_variant<128, 2, 2, 3, 2, EPI_ACT_RGB, false>(ta, tw, p, st);
+}
+
+}  // namespace l2i

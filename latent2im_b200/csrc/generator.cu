@@ -94,6 +94,7 @@ int run_conv(l2i_generator* g, const StyledConvLayer& L, const void* in, const C
   const bool want_tc = g->conv_impl != 1;
   if (want_tc && !L.split && L.w_quad != nullptr && !geom.in_pair_packed && conv_tc_quad_supported(geom, e))
     return launch_conv_tc_quad(in, L.w_quad, geom, e, st);
+  if (want_tc && !L.split && conv_tc_ares_supported(geom, e)) return launch_conv_tc_ares(in, L.w_bf16, geom, e, st);
   if (want_tc && !L.split && conv_tc_halo_supported(geom, e) && (geom.Cin != 32 || (L.w_pair != nullptr && geom.in_pair_packed)))
     return launch_conv_tc_halo(in, geom.Cin == 32 ? L.w_pair : L.w_bf16, geom, e, st);
   if (want_tc && conv_tc_supported(geom, e)) {
@@ -459,6 +460,7 @@ extern "C" int l2i_generator_forward(l2i_generator_t* g, const float* latent, in
       auto* sg_c = g->seg_begin(L.name + "/upconv+blur_act", 0, 2.0 * 9 * L.cin * L.cout * px_in,
                                 (px_in * L.cin + px_out * L.cout) * es + px_out * 4.0, st);
       if (conv_tc_halo_supported(geom, e)) L2I_TRY(launch_conv_tc_halo(g->act[cur], L.w_comp, geom, e, st));
+      else if (conv_tc_ares_supported(geom, e)) L2I_TRY(launch_conv_tc_ares(g->act[cur], L.w_comp, geom, e, st));
       else if (conv_tc_supported(geom, e)) L2I_TRY(launch_conv_tc(g->act[cur], L.w_comp, geom, e, st));
       else { set_error("generator: composite up-conv of %s is not supported by the tcgen05 kernels", L.name.c_str()); return L2I_ERR_UNSUPPORTED; }
       g->seg_end(sg_c, st);

@@ -16,6 +16,8 @@ int conv_tc_block_n(const ConvGeom& g);
 bool conv_tc_halo_supported(const ConvGeom& g, const EpiParams& e);
 int launch_conv_tc_halo(const void* in, const __nv_bfloat16* w, const ConvGeom& g, const EpiParams& e, cudaStream_t st);
 int launch_pack_pair_weight(__nv_bfloat16* dst, const float* src, int Cout, float scale, cudaStream_t st);
+bool conv_tc_ares_supported(const ConvGeom& g, const EpiParams& e);
+int launch_conv_tc_ares(const void* in, const __nv_bfloat16* w, const ConvGeom& g, const EpiParams& e, cudaStream_t st);
 bool conv_tc_quad_supported(const ConvGeom& g, const EpiParams& e);
 int launch_conv_tc_quad(const void* in, const __nv_bfloat16* w, const ConvGeom& g, const EpiParams& e, cudaStream_t st);
 int launch_pack_quad_weight(__nv_bfloat16* dst, const float* src, float scale, cudaStream_t st);
