@@ -260,3 +260,21 @@ def test_full_size_bf16_vs_fp32_kernels(size, batch):
         out[dt], _ = gen(lat, input_is_latent=True, noise=noise)
     assert torch.isfinite(out[torch.bfloat16]).all()
     assert _psnr(out[torch.bfloat16].double(), out[torch.float32].double()) >= 45.0
+
+
+@pytest.mark.parametrize("size,cm,batch", [(128, 2, 3), (256, 1, 2), (512, 1, 1), (512, 2, 2), (1024, 1, 1)])
+def test_kernel_selection_sweep_bf16_vs_fp32(size, cm, batch):
+    """Every (resolution, channel multiplier) routes layers to different tcgen05 kernels (general, halo-resident,
+    A-resident, composite, 2x2-block, pair-packed); odd batches exercise the per-sample epilogue vector restaging.
+    Gate: bf16 PSNR >= 45 dB against the fp32 CUDA-core path."""
+    from latent2im_b200.graphs.stylegan_v2_real.networks import Generator
+    gen = load_synthetic(Generator(size, 512, 2, channel_multiplier=cm), seed=3).cuda()
+    z = torch.tensor(synthetic_z(batch, 1), dtype=torch.float32).cuda()
+    lat = gen.style(z)[:, None, :].repeat(1, gen.n_latent, 1)
+    noise = [n.cuda() for n in synthetic_noise(gen.num_layers, batch)]
+    out = {}
+    for dt in (torch.float32, torch.bfloat16):
+        gen.set_native(dtype=dt)
+        out[dt], _ = gen(lat, input_is_latent=True, noise=noise)
+    assert torch.isfinite(out[torch.bfloat16]).all()
+    assert _psnr(out[torch.bfloat16].double(), out[torch.float32].double()) >= 45.0
