@@ -438,12 +438,23 @@ int launch_conv_tc(const void* in, const __nv_bfloat16* w, const ConvGeom& g, co
   p.OH = g.OH; p.OW = g.OW; p.nphase = g.nphase; p.out_scale = g.out_scale; p.out_H = g.out_H; p.out_W = g.out_W;
   for (int i = 0; i < 4; ++i) p.taps[i] = g.taps[i];
   p.e = e;
-  // M-tile box: up to 16 pixels wide, then rows, always inside one sample (<= 128 rows; tiny
-  // resolutions leave TMEM lanes unused, which costs nothing that matters)
-  int bw = 1;
-  while (bw < 16 && bw < g.OW) bw <<= 1;
-  int bh = 1;
-  while (bw * bh < 128 && bh < g.OH) bh <<= 1;
+  // M-tile box: bw x bh pixels of one sample, bw * bh <= 128 GEMM rows.  Power-of-two boxes (16 x 8) tile the
+  // power-of-two image sizes exactly; the phase grids of the stride-2 layers are (H+1)^2 = 5, 9, 17, 33, 65, 129 wide,
+  // where a fixed 16 x 8 box wastes up to 62 % of the MMA rows, so the box is chosen to minimise the tile count
+  // (ties: prefer the widest box, whose rows are the longest contiguous runs in memory).
+  int bw = 1, bh = 1;
+  {
+    int64_t best = -1;
+    for (int w = 1; w <= std::min(g.OW, 128); ++w) {
+      const int h = std::min(g.OH, 128 / w);
+      const int64_t tiles = (int64_t)ceil_div(g.OW, w) * ceil_div(g.OH, h);
+      const bool pow2 = (w & (w - 1)) == 0;
+      // an exact power-of-two tiling keeps the 16 x 8 shape the epilogue's coalescing was tuned for
+      if (best < 0 || tiles < best || (tiles == best && (pow2 && w <= 16 ? w >= bw || (bw & (bw - 1)) != 0 : (bw & (bw - 1)) != 0 && w > bw))) {
+        best = tiles; bw = w; bh = h;
+      }
+    }
+  }
   p.bw = bw; p.bh = bh;
   p.tiles_x = ceil_div(g.OW, bw); p.tiles_y = ceil_div(g.OH, bh);
   const int bn = pick_block_n(g.Cout);
