@@ -1,5 +1,7 @@
 // Library-level entry points: ABI version, thread-local error string, launch counter.
-#include "common.cuh"
+#include <cstdlib>
+
+#include "conv_common.cuh"
 
 namespace l2i {
 
@@ -11,6 +13,23 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+KernelSwitches g_switches;
+
+void refresh_kernel_switches() {
+  auto flag = [](const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return v == nullptr ? dflt : std::atoi(v);
+  };
+  KernelSwitches s;
+  s.halo = flag("L2I_HALO", 1) != 0;
+  s.halo_mask = flag("L2I_HALO_MASK", 15);
+  s.halo_base_offset = flag("L2I_HALO_BASE_OFFSET", 0) != 0;
+  s.quad = flag("L2I_QUAD", 1) != 0;
+  s.ares = flag("L2I_ARES", 1) != 0;
+  s.fir_simt = flag("L2I_FIR_SIMT", 0) != 0;
+  g_switches = s;
 }
 
 }  // namespace l2i

@@ -389,7 +389,7 @@ int backward_impl(l2i_generator* g, float* grad_latent, const float* grad_image,
       L2I_TRY(launch_act_bwd<T>(g->gbuf, g_xn, nullptr, L.y_save, s_next, g->s_rows, nullptr, 0, nullptr, 0, nullptr, 0, nullptr,
                                 nullptr, g->R_s + L.d_off, nullptr, R_bs, nullptr, 0, B, HWo, L.cout, st));
       const int TH = 2 * L.res_in + 2;
-      if (sizeof(T) == 2 && fir_tma_supported(L.cout) && !std::getenv("L2I_FIR_SIMT"))
+      if (sizeof(T) == 2 && fir_tma_supported(L.cout))
         L2I_TRY(launch_blur_bwd_tma(g->tbuf, g->gbuf, L.t_save, demod, g->d_rows, g->R_d + L.d_off, R_bs, B, L.res_out, L.res_out, TH, TH,
                                     L.cout, g->fir, st));
       else

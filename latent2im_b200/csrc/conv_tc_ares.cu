@@ -293,12 +293,7 @@ int launch_ares_variant(const CUtensorMap& ta, const CUtensorMap& tw, const Ares
 }  // namespace
 
 bool conv_tc_ares_supported(const ConvGeom& g, const EpiParams& e) {
-  static int enabled = -1;
-  if (enabled < 0) {
-    const char* env = std::getenv("L2I_ARES");
-    enabled = (env != nullptr && env[0] == '0') ? 0 : 1;
-  }
-  if (!enabled || !tmap_available()) return false;
+  if (!g_switches.ares || !tmap_available()) return false;
   if (g.nphase != 1 || g.in_scale != 1 || g.weight_taps != 9 || g.in_pair_packed || g.out_pair_packed) return false;
   if (g.Cin != 128 || g.H < 16 || g.W < 16 || e.mode != 0) return false;
   if (g.up_cout > 0) return g.up_cout == 64 && g.Cout == 256 && e.wr == nullptr;

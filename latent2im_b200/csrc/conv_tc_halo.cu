@@ -381,22 +381,14 @@ int launch_halo_variant(const CUtensorMap& ta, const CUtensorMap& tw, const CUte
   return check_launch("conv_tc_halo");
 }
 
-int g_halo_enabled = -1, g_halo_boff = 0, g_halo_mask = 15;
 
 }  // namespace
 
 // Which layers this kernel takes: plain 64->64 / 64->32 ... with Cin == 64, Cout in {32, 64}; the
 // stride-2 transposed conv with Cin == 64; and Cin == 32 -> 32 plain through the pair-packed view.
 bool conv_tc_halo_supported(const ConvGeom& g, const EpiParams& e) {
-  if (g_halo_enabled < 0) {
-    const char* env = std::getenv("L2I_HALO");
-    g_halo_enabled = (env != nullptr && env[0] == '0') ? 0 : 1;
-    const char* bo = std::getenv("L2I_HALO_BASE_OFFSET");
-    if (bo != nullptr) g_halo_boff = bo[0] != '0';
-    const char* mk = std::getenv("L2I_HALO_MASK");   // bit 0 plain Cin=64, bit 1 up-conv, bit 2 pair-packed Cin=32, bit 3 composite up-conv
-    if (mk != nullptr) g_halo_mask = std::atoi(mk);
-  }
-  if (!g_halo_enabled || !tmap_available()) return false;
+  const int g_halo_mask = g_switches.halo_mask;
+  if (!g_switches.halo || !tmap_available()) return false;
   if (g.in_scale != 1 || g.weight_taps != 9) return false;
   if (g.H < 16 || g.W < 16) return false;
   if (g.up_cout > 0)   // composite up-conv 64 -> 32: GEMM N = 128, weights (9 x 16 KB) resident
@@ -415,7 +407,7 @@ int launch_conv_tc_halo(const void* in, const __nv_bfloat16* w, const ConvGeom& 
   HaloParams p{};
   p.B = g.B; p.Cout = g.Cout; p.out_H = g.out_H; p.out_W = g.out_W; p.e = e;
   p.pair_out = g.out_pair_packed;
-  p.base_offset_mode = g_halo_boff;
+  p.base_offset_mode = g_switches.halo_base_offset;
   p.idesc = make_idesc_bf16(128, g.Cout, 0);
   const bool pair = g.Cin == 32;
   const bool comp = g.up_cout > 0;

@@ -344,12 +344,7 @@ __global__ void pack_quad_weight_kernel(__nv_bfloat16* __restrict__ dst, const f
 // The 2x2-block kernel takes plain (non-transposed) 32 -> 32 convs with the act + ToRGB epilogue on even-sized images
 // stored as plain NHWC (64 bytes per pixel).
 bool conv_tc_quad_supported(const ConvGeom& g, const EpiParams& e) {
-  static int enabled = -1;
-  if (enabled < 0) {
-    const char* env = std::getenv("L2I_QUAD");
-    enabled = (env != nullptr && env[0] == '0') ? 0 : 1;
-  }
-  if (!enabled || !tmap_available()) return false;
+  if (!g_switches.quad || !tmap_available()) return false;
   if (g.nphase != 1 || g.in_scale != 1 || g.up_cout != 0 || g.in_pair_packed) return false;
   if (g.Cin != 32 || g.Cout != 32 || e.mode != 0 || e.wr == nullptr) return false;
   if (g.H < 32 || g.W < 16 || (g.H & 1) || (g.W & 1) || g.OH != g.H || g.OW != g.W) return false;

@@ -172,7 +172,7 @@ int launch_fir_variant(const void* in, int in_H, int in_W, FirParams& p, cudaStr
 
 }  // namespace
 
-bool fir_tma_supported(int C) { return tmap_available() && C % 32 == 0; }
+bool fir_tma_supported(int C) { return !g_switches.fir_simt && tmap_available() && C % 32 == 0; }
 
 // Forward: t [B][TH][TW][C] fp16 -> out [B][OH][OW][C] bf16 (optionally pair-packed), y_out optional.
 int launch_blur_act_tma(void* out, void* y_out, const void* t, int B, int OH, int OW, int C, int TH, int TW, const float* noise,

@@ -130,6 +130,7 @@ extern "C" int l2i_generator_create(l2i_generator_t** out, int size, int style_d
   L2I_REQUIRE(blur_taps != nullptr && n_blur_taps == 4,
               "generator_create: the fused up-conv/blur path needs a 4-tap separable blur kernel (got %d taps)", n_blur_taps);
 
+  refresh_kernel_switches();
   l2i_generator* g = new l2i_generator();
   g->size = size; g->D = style_dim; g->n_mlp = n_mlp; g->cm = channel_multiplier; g->dtype = dtype;
   g->max_batch = max_batch; g->lr_mlp = lr_mlp;
@@ -485,7 +486,7 @@ extern "C" int l2i_generator_forward(l2i_generator_t* g, const float* latent, in
       const bool pair_next = !f32 && next != nullptr && layer_uses_pair_halo(g, *next, B);
       if (f32) L2I_TRY(launch_blur_act<float, float>(dst, keep ? L.y_save : nullptr, tdst, B, L.res_out, L.res_out, L.cout, geom.out_H, geom.out_W, nz, nz_bs, nz_w,
                                               P(g, L.name + ".activate.bias"), s_next, g->s_rows, g->fir, 0, st));
-      else if (fir_tma_supported(L.cout) && !std::getenv("L2I_FIR_SIMT"))
+      else if (fir_tma_supported(L.cout))
         L2I_TRY(launch_blur_act_tma(dst, keep ? L.y_save : nullptr, tdst, B, L.res_out, L.res_out, L.cout, geom.out_H, geom.out_W, nz, nz_bs,
                                     nz_w, P(g, L.name + ".activate.bias"), s_next, g->s_rows, g->fir, pair_next ? 1 : 0, st));
       else L2I_TRY(launch_blur_act<__nv_bfloat16, __half>(dst, keep ? L.y_save : nullptr, tdst, B, L.res_out, L.res_out, L.cout, geom.out_H, geom.out_W, nz, nz_bs,

@@ -278,3 +278,24 @@ def test_kernel_selection_sweep_bf16_vs_fp32(size, cm, batch):
         out[dt], _ = gen(lat, input_is_latent=True, noise=noise)
     assert torch.isfinite(out[torch.bfloat16]).all()
     assert _psnr(out[torch.bfloat16].double(), out[torch.float32].double()) >= 45.0
+
+
+@pytest.mark.parametrize("env", [{"L2I_QUAD": "0"}, {"L2I_ARES": "0"}, {"L2I_FIR_SIMT": "1"}, {"L2I_HALO": "0", "L2I_QUAD": "0"},
+                                 {"L2I_COMPOSITE_RES": "4096"}])
+def test_fallback_kernel_paths_stay_correct(env, monkeypatch):
+    """The kernel-selection switches (read at every generator create) route the same layers through the older kernels:
+    pair-packed halo instead of the 2x2-block kernel, the general kernel instead of the A-resident / halo-resident ones,
+    the register-window FIR, and the two-kernel transposed conv + blur instead of the composite conv."""
+    from latent2im_b200.graphs.stylegan_v2_real.networks import Generator
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    size, batch = 512, 1
+    gen = load_synthetic(Generator(size, 512, 2, channel_multiplier=1), seed=3).cuda()
+    z = torch.tensor(synthetic_z(batch, 1), dtype=torch.float32).cuda()
+    lat = gen.style(z)[:, None, :].repeat(1, gen.n_latent, 1)
+    noise = [n.cuda() for n in synthetic_noise(gen.num_layers, batch)]
+    out = {}
+    for dt in (torch.float32, torch.bfloat16):
+        gen.set_native(dtype=dt)
+        out[dt], _ = gen(lat, input_is_latent=True, noise=noise)
+    assert _psnr(out[torch.bfloat16].double(), out[torch.float32].double()) >= 45.0
