@@ -28,6 +28,7 @@ void refresh_kernel_switches() {
   s.halo_base_offset = flag("L2I_HALO_BASE_OFFSET", 0) != 0;
   s.quad = flag("L2I_QUAD", 1) != 0;
   s.ares = flag("L2I_ARES", 1) != 0;
+  s.vpair = flag("L2I_VPAIR", 1) != 0;
   s.fir_simt = flag("L2I_FIR_SIMT", 0) != 0;
   g_switches = s;
 }

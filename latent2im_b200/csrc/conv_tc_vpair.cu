@@ -1,0 +1,344 @@
+// Vertical-pair tcgen05 implicit-GEMM conv for the plain 64 -> 64 channel 3x3 layer (512 x 512 px).
+//
+// Issued tap by tap this layer is N = 64 per MMA, and an M = 128 tcgen05.mma costs ~64-77 clocks per K = 16 step
+// whatever N <= 128 is (A rows stream at 2 / clock), so the tensor pipe runs at half rate (conv_tc_halo.cu: 36 MMAs per
+// 128 pixels).  Here one GEMM row is a VERTICAL PAIR of output pixels (rows 2j, 2j+1 of one column):
+//     N = 128 = (parity, co);  the pair reads input rows 2j-1+r, r = 0..3, and columns x-1+kw, kw = 0..2
+//     parity p takes input row r with kernel row kh = r - p  ->  r = 0: (p0, kh0);  r = 1: (p0, kh1), (p1, kh0);
+//                                                               r = 2: (p0, kh2), (p1, kh1);  r = 3: (p1, kh2)
+// i.e. 12 (r, kw) steps x 4 K16 = 48 MMAs per 256 pixels instead of 72.  The B operand needs no zero padding and no
+// duplicated weights: the nine 64 x 64 weight tiles are stored per kw in the order W[kh=2], W[kh=1], W[kh=0], so the
+// N = 128 operand of r = 1 is the 16 KB window starting at W[kh=1] and that of r = 2 the window starting at W[kh=2]
+// (overlapping UMMA descriptors); r = 0 and r = 3 are N = 64 MMAs into the lower / upper half of the accumulator.
+// A comes straight from the NHWC halo tile (TMA, once per output tile): GEMM rows of one 8-row group are 8 adjacent
+// pixels (128 B apart), groups are two image rows apart (stride-byte-offset = 2 x halo pitch).
+#include "tc_epilogue.cuh"
+
+namespace l2i {
+
+using namespace tc;
+
+namespace {
+
+constexpr int kVW = 10, kVH = 34;                          // halo tile: (8 + 2) x (32 + 2) pixels of 64 channels
+constexpr int kVHaloBytes = kVW * kVH * 128;               // 43520
+constexpr int kVStageBytes = (kVHaloBytes + 1023) & ~1023;
+constexpr int kVStages = 2;
+constexpr int kVGroups = 3;                               // 512 threads -> 128 registers per thread
+constexpr int kVThreads = 128 + kVGroups * 128;
+constexpr int kVWBytes = 9 * 64 * 128;                     // 73728: nine 64 x 64 bf16 tiles
+constexpr int kVStageOutBytes = 2048;                      // per epilogue warp: 32 pixels x 32 channels, SWIZZLE_64B (TMA store source)
+constexpr int kVSmem = kVStages * kVStageBytes + kVWBytes + kVGroups * 4 * kVStageOutBytes + 1024;
+constexpr int kVTileW = 8, kVTileH = 32;
+
+struct VPairParams {
+  int B, H, W;
+  int tiles_x, tiles_y, total_tiles;
+  uint32_t idesc128, idesc64;
+  int tma_store;             // activation output goes through per-warp staging tiles + strided TMA tensor stores
+  EpiParams e;
+};
+
+__device__ __forceinline__ uint64_t vp_desc(uint32_t addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void vp_group_sync(int group) {
+  asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+}
+
+__global__ void __launch_bounds__(kVThreads, 1)
+conv_tc_vpair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                     const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ VPairParams p) {
+  constexpr int N = 128, CO = 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem_w = smem + kVStages * kVStageBytes;
+  uint8_t* smem_stage_out = smem_w + kVWBytes;
+  __shared__ __align__(16) float epi_smem[kVGroups * 6 * CO];
+  __shared__ __align__(8) uint64_t full_bar[kVStages];
+  __shared__ __align__(8) uint64_t empty_bar[kVStages];
+  __shared__ __align__(8) uint64_t tmem_full[kVGroups];
+  __shared__ __align__(8) uint64_t tmem_empty[kVGroups];
+  __shared__ __align__(8) uint64_t w_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_w);
+    if (p.tma_store) prefetch_tmap(&tmap_o);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kVStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < kVGroups; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+    mbar_init(&w_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  auto decode = [&](int tile, int& x0, int& y0, int& b) {
+    const int tx = tile % p.tiles_x;
+    const int r = tile / p.tiles_x;
+    const int ty = r % p.tiles_y;
+    b = r / p.tiles_y;
+    x0 = tx * kVTileW; y0 = ty * kVTileH;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer: the nine weight tiles once, then one halo tile per output tile ===
+    if (lane == 0) {
+      mbar_expect_tx(&w_bar, (uint32_t)kVWBytes);
+      for (int t = 0; t < 9; ++t) tma_load_3d(smem_w + t * (64 * 128), &tmap_w, &w_bar, 0, 0, t);
+      int stage = 0;
+      uint32_t phase_bit = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int x0, y0, b;
+        decode(tile, x0, y0, b);
+        mbar_wait(&empty_bar[stage], phase_bit ^ 1);
+        mbar_expect_tx(&full_bar[stage], kVHaloBytes);
+        tma_load_4d(smem + stage * kVStageBytes, &tmap_a, &full_bar[stage], 0, x0 - 1, y0 - 1, b);
+        if (++stage == kVStages) { stage = 0; phase_bit ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: 48 MMAs per tile, no barrier inside a tile =====================
+    if (lane == 0) {
+      mbar_wait(&w_bar, 0);
+      tc_fence_after();
+      const uint32_t w_base = smem_u32(smem_w);
+      int stage = 0, grp = 0;
+      uint32_t phase_bit = 0, grp_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[grp], grp_phase ^ 1);
+        mbar_wait(&full_bar[stage], phase_bit);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smem + stage * kVStageBytes);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(grp * N);
+        // input-row order 1, 2, 0, 3: the first MMA (r = 1, N = 128) initialises all 128 accumulator columns
+#pragma unroll
+        for (int ri = 0; ri < 4; ++ri) {
+          const int r = ri == 0 ? 1 : (ri == 1 ? 2 : (ri == 2 ? 0 : 3));
+          // weight window: slots per kw are W[kh=2], W[kh=1], W[kh=0]; parity 0 uses kh = r, parity 1 kh = r - 1
+          const int slot = r == 0 ? 2 : (r == 1 ? 1 : 0);            // first 64-row slot of the operand
+          const bool wide = (r == 1 || r == 2);                      // N = 128 (both parities) or N = 64
+          const uint32_t d_col = r == 3 ? 64u : 0u;                  // r = 3 feeds parity 1 only
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const uint32_t a_tap = a_base + (uint32_t)((r * kVW + kw) * 128);
+            const uint32_t b_tap = w_base + (uint32_t)((kw * 3 + slot) * (64 * 128));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_d + d_col, vp_desc(a_tap + k * 32, 2 * kVW * 128), vp_desc(b_tap + k * 32, 1024),
+                        wide ? p.idesc128 : p.idesc64, (ri | kw | k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        umma_commit(&tmem_full[grp]);
+        if (++stage == kVStages) { stage = 0; phase_bit ^= 1; }
+        if (++grp == kVGroups) { grp = 0; grp_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: thread = one column x two rows (parity = accumulator half) ==========
+    const EpiParams& e = p.e;
+    const int group = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int gtid = threadIdx.x - (128 + group * 128);
+    float* sp = epi_smem + group * (6 * CO);
+    float* s_d = sp;
+    float* s_b = sp + CO;
+    float* s_n = sp + 2 * CO;
+    float* s_w = sp + 3 * CO;
+    constexpr float kSqrt2 = 1.4142135623730951f;
+    const float nw = (e.noise != nullptr && e.noise_w != nullptr) ? __ldg(e.noise_w) * kSqrt2 : 0.f;
+    const int64_t plane = (int64_t)p.H * p.W;
+    const int lx = row & 7, lj = row >> 3;
+    uint32_t grp_phase = 0;
+    int staged_b = -1;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      if (it % kVGroups != group) continue;
+      int x0, y0, b;
+      decode(tile, x0, y0, b);
+      const int X = x0 + lx, Y = y0 + 2 * lj;              // upper pixel of the pair
+      const bool ok = X < p.W && Y < p.H;                   // H is even: both pixels inside or both outside
+
+      if (b != staged_b) {
+        vp_group_sync(group);
+        for (int j = gtid; j < CO; j += 128) {
+          s_d[j] = (e.demod != nullptr ? __ldg(e.demod + (int64_t)b * e.demod_bs + j) : 1.f) * kSqrt2;
+          s_b[j] = __ldg(e.bias + j) * kSqrt2;
+          s_n[j] = e.s_next ? __ldg(e.s_next + (int64_t)b * e.s_next_bs + j) : 1.f;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) s_w[c * CO + j] = e.wr ? __ldg(e.wr + (int64_t)b * e.wr_bs + c * CO + j) : 0.f;
+        }
+        vp_group_sync(group);
+        staged_b = b;
+      }
+
+      float nzp[2] = {0.f, 0.f};
+      float up[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+      if (ok) {
+        if (e.noise != nullptr) {
+          const float* np = e.noise + (int64_t)b * e.noise_bs + (int64_t)Y * p.W + X;
+          nzp[0] = nw * __ldg(np);
+          nzp[1] = nw * __ldg(np + p.W);
+        }
+        if (e.fused_skip) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float bias_c = __ldg(e.rgb_bias + c);
+            up[0][c] = up[1][c] = bias_c;
+            if (e.skip_in != nullptr) {
+              const float* pl = e.skip_in + ((int64_t)b * 3 + c) * (plane >> 2);
+              up[0][c] += upsample2x_at(pl, p.H >> 1, p.W >> 1, Y, X, e.fir);
+              up[1][c] += upsample2x_at(pl, p.H >> 1, p.W >> 1, Y + 1, X, e.fir);
+            }
+          }
+        }
+      }
+
+      mbar_wait(&tmem_full[group], grp_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(group * N);
+      float rgb[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+      uint8_t* stage_tile = smem_stage_out + (warp - 4) * kVStageOutBytes;
+      __nv_bfloat16* stage_row = (__nv_bfloat16*)stage_tile + lane * 32;     // this lane's 64-byte row of the staging tile
+      const int stage_swz = (lane >> 1) & 3;                                 // SWIZZLE_64B: 16-byte chunk ^= address bits [7:8]
+      const bool want_out = e.out != nullptr && e.s_next != nullptr;
+#pragma unroll 1
+      for (int cs = 0; cs < CO; cs += 32) {     // 32 channels of BOTH pixels of the pair: the per-channel vectors are fetched once
+        uint32_t v0[32], v1[32];
+        tmem_ld32(taddr + cs, v0);
+        tmem_ld32(taddr + CO + cs, v1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int par = 0; par < 2; ++par) {
+          __nv_bfloat16* outc = nullptr;
+          __nv_bfloat16* yc = nullptr;
+          const int64_t pix = ((int64_t)b * p.H + Y + par) * p.W + X;
+          if (ok && e.y_out != nullptr) yc = (__nv_bfloat16*)e.y_out + pix * CO + cs;
+          if (want_out && p.tma_store) {
+            if (lane == 0) tma_store_wait_read();     // the previous store has finished reading this warp's staging tile
+            __syncwarp();
+            outc = stage_row;
+          } else if (ok && want_out) {
+            outc = (__nv_bfloat16*)e.out + pix * CO + cs;
+          }
+          epilogue_chunk32<EPI_ACT_RGB>(par == 0 ? v0 : v1, s_d + cs, s_b + cs, s_n + cs, s_w + cs, s_w + CO + cs, s_w + 2 * CO + cs,
+                                        nzp[par], false, rgb[par][0], rgb[par][1], rgb[par][2], outc, yc,
+                                        (want_out && p.tma_store) ? stage_swz : 0);
+          if (want_out && p.tma_store) {
+            // the warp's 4 pair-rows x 8 columns of this parity = every other image row: one strided TMA tensor store
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tma_store_4d(&tmap_o, stage_tile, cs, x0, y0 + 8 * q + par, b);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[group]);
+      grp_phase ^= 1;
+
+      if (e.wr != nullptr && ok) {
+        float* dst = e.fused_skip ? e.skip_out : e.rgb_part;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float* pl = dst + ((int64_t)b * 3 + c) * plane + (int64_t)Y * p.W + X;
+          pl[0] = rgb[0][c] + up[0][c];
+          pl[p.W] = rgb[1][c] + up[1][c];
+        }
+      }
+    }
+  }
+
+  if (p.tma_store && warp >= 4 && lane == 0) tma_store_wait_all();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// dst [kw][2 - kh][co][ci] bf16 (tile t = kw*3 + (2 - kh)); src [64 co][64 ci][3][3] fp32
+__global__ void pack_vpair_weight_kernel(__nv_bfloat16* __restrict__ dst, const float* __restrict__ src, float scale) {
+  const int total = 9 * 64 * 64;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int ci = idx % 64, co = (idx / 64) % 64, t = idx / 4096;
+    const int kw = t / 3, kh = 2 - t % 3;
+    dst[idx] = __float2bfloat16_rn(src[(((int64_t)co * 64 + ci) * 3 + kh) * 3 + kw] * scale);
+  }
+}
+
+}  // namespace
+
+bool conv_tc_vpair_supported(const ConvGeom& g, const EpiParams& e) {
+  if (!g_switches.vpair || !tmap_available()) return false;
+  if (g.nphase != 1 || g.in_scale != 1 || g.up_cout != 0 || g.in_pair_packed || g.weight_taps != 9) return false;
+  if (g.Cin != 64 || g.Cout != 64 || e.mode != 0 || e.wr == nullptr || !e.fused_skip) return false;
+  if (g.H < 32 || g.W < 8 || (g.H & 1) || g.OH != g.H || g.OW != g.W) return false;
+  return true;
+}
+
+int launch_pack_vpair_weight(__nv_bfloat16* dst, const float* src, float scale, cudaStream_t st) {
+  pack_vpair_weight_kernel<<<ceil_div(9 * 64 * 64, 256), 256, 0, st>>>(dst, src, scale);
+  return check_launch("pack_vpair_weight");
+}
+
+// w: the [9][64][64] bf16 tiles written by launch_pack_vpair_weight
+int launch_conv_tc_vpair(const void* in, const __nv_bfloat16* w, const ConvGeom& g, const EpiParams& e, cudaStream_t st) {
+  VPairParams p{};
+  p.B = g.B; p.H = g.H; p.W = g.W; p.e = e;
+  p.idesc128 = make_idesc_bf16(128, 128, 0);
+  p.idesc64 = make_idesc_bf16(128, 64, 0);
+  CUtensorMap ta, tw;
+  {
+    const uint64_t dims[4] = {64, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
+    const uint64_t str[4] = {2, 128, (uint64_t)g.W * 128, (uint64_t)g.H * g.W * 128};
+    const uint32_t box[4] = {64, kVW, kVH, 1};
+    L2I_TRY(make_tmap(&ta, in, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  {
+    const uint64_t dims[3] = {64, 64, 9};
+    const uint64_t str[3] = {2, 128, 64 * 128};
+    const uint32_t box[3] = {64, 64, 1};
+    L2I_TRY(make_tmap(&tw, w, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  CUtensorMap to = ta;
+  p.tma_store = 0;
+  if (e.out != nullptr && e.s_next != nullptr && e.y_out == nullptr && (uintptr_t)e.out % 16 == 0) {
+    // a warp's 32 pixels of one parity: 8 columns x 4 rows, rows two apart; 32 of the 64 channels per store
+    const uint64_t dims[4] = {64, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
+    const uint64_t str[4] = {2, 128, (uint64_t)g.W * 128, (uint64_t)g.H * g.W * 128};
+    const uint32_t box[4] = {32, 8, 8, 1};
+    const uint32_t estr[4] = {1, 1, 2, 1};
+    L2I_TRY(make_tmap_strided(&to, e.out, 4, dims, str, box, estr, CU_TENSOR_MAP_SWIZZLE_64B));
+    p.tma_store = 1;
+  }
+  p.tiles_x = ceil_div(g.W, kVTileW); p.tiles_y = ceil_div(g.H, kVTileH);
+  const int64_t total = (int64_t)p.tiles_x * p.tiles_y * g.B;
+  if (total <= 0 || total > 0x7fffffff) { set_error("conv_tc_vpair: bad tile count"); return L2I_ERR_INVALID_ARG; }
+  p.total_tiles = (int)total;
+  static bool attr_set = false;
+  if (!attr_set) {
+    L2I_CUDA_TRY(cudaFuncSetAttribute(conv_tc_vpair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kVSmem));
+    attr_set = true;
+  }
+  const int grid = std::min(p.total_tiles, kNumSMs);
+  conv_tc_vpair_kernel<<<grid, kVThreads, kVSmem, st>>>(ta, tw, to, p);
+  return check_launch("conv_tc_vpair");
+}
+
+}  // namespace l2i

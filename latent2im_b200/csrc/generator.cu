@@ -95,6 +95,7 @@ int run_conv(l2i_generator* g, const StyledConvLayer& L, const void* in, const C
   if (want_tc && !L.split && L.w_quad != nullptr && !geom.in_pair_packed && conv_tc_quad_supported(geom, e))
     return launch_conv_tc_quad(in, L.w_quad, geom, e, st);
   if (want_tc && !L.split && conv_tc_ares_supported(geom, e)) return launch_conv_tc_ares(in, L.w_bf16, geom, e, st);
+  if (want_tc && !L.split && L.w_vpair != nullptr && conv_tc_vpair_supported(geom, e)) return launch_conv_tc_vpair(in, L.w_vpair, geom, e, st);
   if (want_tc && !L.split && conv_tc_halo_supported(geom, e) && (geom.Cin != 32 || (L.w_pair != nullptr && geom.in_pair_packed)))
     return launch_conv_tc_halo(in, geom.Cin == 32 ? L.w_pair : L.w_bf16, geom, e, st);
   if (want_tc && conv_tc_supported(geom, e)) {
@@ -252,6 +253,7 @@ extern "C" int l2i_generator_create(l2i_generator_t** out, int size, int style_d
     if (rc == L2I_OK && dtype == L2I_BF16) rc = dev_alloc(g, &L.w_bf16, (int64_t)(L.split ? 18 : 9) * L.cin * L.cout);
     if (rc == L2I_OK && dtype == L2I_BF16 && L.cin == 32 && !L.up) rc = dev_alloc(g, &L.w_pair, (int64_t)12 * L.cout * 64);
     if (rc == L2I_OK && dtype == L2I_BF16 && L.cin == 32 && L.cout == 32 && !L.up) rc = dev_alloc(g, &L.w_quad, (int64_t)128 * 512);
+    if (rc == L2I_OK && dtype == L2I_BF16 && L.cin == 64 && L.cout == 64 && !L.up) rc = dev_alloc(g, &L.w_vpair, (int64_t)9 * 64 * 64);
     L.composite = dtype == L2I_BF16 && L.up && g->conv_impl != 1 && L.res_out >= g->composite_min_res && L.cout % 32 == 0 &&
                   L.cin % 64 == 0;
     if (rc == L2I_OK && L.composite) rc = dev_alloc(g, &L.w_comp, (int64_t)36 * L.cin * L.cout);
@@ -345,6 +347,7 @@ extern "C" int l2i_generator_finalize(l2i_generator_t* g, void* stream) {
     L2I_TRY(launch_pack_conv_weight(L.w_f32, L.w_bf16, g->wsq_all + L.wsq_off, P(g, L.name + ".conv.weight"), L.cout,
                                     L.cin, 9, scale, L.split ? 1 : 0, st));
     if (L.w_pair) L2I_TRY(launch_pack_pair_weight(L.w_pair, P(g, L.name + ".conv.weight"), L.cout, scale, st));
+    if (L.w_vpair) L2I_TRY(launch_pack_vpair_weight(L.w_vpair, P(g, L.name + ".conv.weight"), scale, st));
     if (L.w_quad) L2I_TRY(launch_pack_quad_weight(L.w_quad, P(g, L.name + ".conv.weight"), scale, st));
     if (L.w_comp) L2I_TRY(launch_pack_composite_weight(L.w_comp, P(g, L.name + ".conv.weight"), L.cout, L.cin, scale, g->fir, st));
     L2I_TRY(launch_scale_copy(g->mod_w_all + (int64_t)L.s_off * D, P(g, L.name + ".conv.modulation.weight"),

@@ -18,6 +18,9 @@ int launch_conv_tc_halo(const void* in, const __nv_bfloat16* w, const ConvGeom& 
 int launch_pack_pair_weight(__nv_bfloat16* dst, const float* src, int Cout, float scale, cudaStream_t st);
 bool conv_tc_ares_supported(const ConvGeom& g, const EpiParams& e);
 int launch_conv_tc_ares(const void* in, const __nv_bfloat16* w, const ConvGeom& g, const EpiParams& e, cudaStream_t st);
+bool conv_tc_vpair_supported(const ConvGeom& g, const EpiParams& e);
+int launch_conv_tc_vpair(const void* in, const __nv_bfloat16* w, const ConvGeom& g, const EpiParams& e, cudaStream_t st);
+int launch_pack_vpair_weight(__nv_bfloat16* dst, const float* src, float scale, cudaStream_t st);
 bool conv_tc_quad_supported(const ConvGeom& g, const EpiParams& e);
 int launch_conv_tc_quad(const void* in, const __nv_bfloat16* w, const ConvGeom& g, const EpiParams& e, cudaStream_t st);
 int launch_pack_quad_weight(__nv_bfloat16* dst, const float* src, float scale, cudaStream_t st);
@@ -58,6 +61,7 @@ struct StyledConvLayer {
   float* w_f32 = nullptr;            // [9][Cin][Cout]
   __nv_bfloat16* w_bf16 = nullptr;   // [9][Cout][Cin], or [18][Cout][Cin] = bf16 hi halves then lo residuals (split)
   __nv_bfloat16* w_pair = nullptr;   // Cin == 32 plain layers: [12][Cout][64] pair-packed tiles for the halo kernel
+  __nv_bfloat16* w_vpair = nullptr;  // 64 -> 64 plain layers: [kw][2-kh][64][64] tiles for the vertical-pair kernel (conv_tc_vpair.cu)
   __nv_bfloat16* w_quad = nullptr;   // 32 -> 32 plain layers: [8][128][64] 2x2-block weight matrix (conv_tc_quad.cu)
   __nv_bfloat16* w_comp = nullptr;   // composite up-conv (transposed conv + blur folded): [9][4*Cout][Cin], rows (phase, co)
   bool composite = false;            // inference forward of this up layer runs the composite kernel (no t intermediate)
