@@ -136,6 +136,154 @@ act_bwd_kernel(T* __restrict__ g_out, const T* __restrict__ g_xn, const float* _
 }
 
 // ------------------------------------------------------------------------------------------------
+// act_bwd, bulk-async variant for the 16-bit path: same maths as act_bwd_kernel, but the two streamed tensors (saved
+// activation y and incoming gradient g_x~') are fetched as contiguous 16 KB tiles with cp.async.bulk into a
+// double-buffered shared-memory ring, so a CTA always has the next tile in flight and the arithmetic reads shared
+// memory.  (The register-window version was load-latency bound: ncu long-scoreboard on the first use of every load.)
+// A tile = P = 8192 / C pixels x C channels; every thread owns one 16-byte channel vector of 4 pixels of the tile.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bw_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bw_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(bw_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(bw_smem_u32(bar))
+               : "memory");
+}
+
+constexpr int kBwTileBytes = 16384;
+
+__global__ void __launch_bounds__(256, 2)
+act_bwd_bulk_kernel(__nv_bfloat16* __restrict__ g_out, const __nv_bfloat16* __restrict__ g_xn, const float* __restrict__ g_rgb,
+                    const __nv_bfloat16* __restrict__ y, const float* __restrict__ s_next, int64_t s_next_bs,
+                    const float* __restrict__ wr, int64_t wr_bs, const float* __restrict__ demod, int64_t demod_bs,
+                    const float* __restrict__ noise, int64_t noise_bs, const float* __restrict__ noise_w,
+                    const float* __restrict__ bias, float* __restrict__ R_s, float* __restrict__ R_d, int64_t R_bs,
+                    float* __restrict__ R_rgb, int64_t R_rgb_bs, int HW, int C, int tiles_per_cta) {
+  using T = __nv_bfloat16;
+  using V = GVec<T, 8>;
+  constexpr float kSqrt2 = 1.4142135623730951f;
+  extern __shared__ __align__(128) uint8_t bw_smem[];
+  uint8_t* ybuf = bw_smem;                                   // [2][16 KB]
+  uint8_t* gbuf = bw_smem + 2 * kBwTileBytes;                // [2][16 KB]
+  float* red = reinterpret_cast<float*>(bw_smem + 4 * kBwTileBytes);   // [5][C]
+  float* prm = red + 5 * C;                                  // [6][C]
+  float *p_sn = prm, *p_dm = prm + C, *p_bs = prm + 2 * C, *p_w0 = prm + 3 * C, *p_w1 = prm + 4 * C, *p_w2 = prm + 5 * C;
+  __shared__ __align__(8) uint64_t bar[2];
+  const int b = blockIdx.y;
+  const int P = kBwTileBytes / (C * 2);                      // pixels per tile
+  const int CV = C / 8, slots = 256 / CV;                    // P == 4 * slots
+  const int cv = threadIdx.x % CV, slot = threadIdx.x / CV;
+  const int c = cv * 8;
+  const int tile0 = blockIdx.x * tiles_per_cta;
+  const int ntiles = min(tiles_per_cta, (HW + P - 1) / P - tile0);
+  const bool has_g = g_xn != nullptr;
+
+  auto issue = [&](int i) {   // thread 0: tile i of this CTA into stage i & 1
+    const int p0 = (tile0 + i) * P;
+    const uint32_t bytes = (uint32_t)(min(P, HW - p0) * C * 2);
+    const int st = i & 1;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bw_smem_u32(&bar[st])), "r"(has_g ? 2 * bytes : bytes) : "memory");
+    bw_bulk_load(ybuf + st * kBwTileBytes, y + ((int64_t)b * HW + p0) * C, bytes, &bar[st]);
+    if (has_g) bw_bulk_load(gbuf + st * kBwTileBytes, g_xn + ((int64_t)b * HW + p0) * C, bytes, &bar[st]);
+  };
+
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bw_smem_u32(&bar[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bw_smem_u32(&bar[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (ntiles > 0) issue(0);
+  }
+  for (int i = threadIdx.x; i < 5 * C; i += 256) red[i] = 0.f;
+  for (int i = threadIdx.x; i < C; i += 256) {
+    p_sn[i] = s_next ? s_next[(int64_t)b * s_next_bs + i] : 0.f;
+    p_dm[i] = demod ? demod[(int64_t)b * demod_bs + i] : 1.f;
+    p_bs[i] = bias ? bias[i] : 0.f;
+    p_w0[i] = wr ? wr[(int64_t)b * wr_bs + i] : 0.f;
+    p_w1[i] = wr ? wr[(int64_t)b * wr_bs + C + i] : 0.f;
+    p_w2[i] = wr ? wr[(int64_t)b * wr_bs + 2 * C + i] : 0.f;
+  }
+  __syncthreads();
+  const float nw = (noise != nullptr && noise_w != nullptr) ? *noise_w : 0.f;
+  float rs[8], rd[8], r0[8], r1[8], r2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) rs[k] = rd[k] = r0[k] = r1[k] = r2[k] = 0.f;
+
+  for (int i = 0; i < ntiles; ++i) {
+    if (threadIdx.x == 0 && i + 1 < ntiles) issue(i + 1);     // stage (i+1)&1 was released by the barrier ending iteration i-1
+    const int st = i & 1;
+    const int p0 = (tile0 + i) * P;
+    // side inputs of this thread's 4 pixels (global, broadcast across the channel vectors), issued before the wait
+    float gr[4][3], nzv[4];
+    bool okp[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = p0 + slot + u * slots;
+      okp[u] = p < HW;
+      const int pc = okp[u] ? p : p0;
+      gr[u][0] = gr[u][1] = gr[u][2] = 0.f;
+      if (g_rgb != nullptr) {
+        gr[u][0] = g_rgb[((int64_t)b * 3 + 0) * HW + pc];
+        gr[u][1] = g_rgb[((int64_t)b * 3 + 1) * HW + pc];
+        gr[u][2] = g_rgb[((int64_t)b * 3 + 2) * HW + pc];
+      }
+      nzv[u] = noise != nullptr ? nw * noise[(int64_t)b * noise_bs + pc] : 0.f;
+    }
+    {
+      const uint32_t parity = (uint32_t)((i >> 1) & 1);
+      asm volatile("{\n.reg .pred P1;\nBWW: mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra BWD;\nbra BWW;\nBWD:\n}" ::"r"(
+                       bw_smem_u32(&bar[st])),
+                   "r"(parity)
+                   : "memory");
+    }
+    const T* ys = reinterpret_cast<const T*>(ybuf + st * kBwTileBytes);
+    const T* gs = reinterpret_cast<const T*>(gbuf + st * kBwTileBytes);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!okp[u]) continue;
+      const int pl = slot + u * slots;
+      const V yv = *reinterpret_cast<const V*>(ys + pl * C + c);
+      V gx;
+      if (has_g) gx = *reinterpret_cast<const V*>(gs + pl * C + c);
+      const float gr0 = gr[u][0], gr1 = gr[u][1], gr2 = gr[u][2], nz = nzv[u];
+      V go;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float yk = __bfloat162float(yv.v[k]);
+        const float gxk = has_g ? __bfloat162float(gx.v[k]) : 0.f;
+        const float gy = p_sn[c + k] * gxk + p_w0[c + k] * gr0 + p_w1[c + k] * gr1 + p_w2[c + k] * gr2;
+        const float gv = gy * (yk > 0.f ? kSqrt2 : 0.2f * kSqrt2);
+        const float v = yk > 0.f ? yk * (1.f / kSqrt2) : yk * (1.f / (0.2f * kSqrt2));
+        rd[k] = fmaf(gv, v - nz - p_bs[c + k], rd[k]);
+        rs[k] = fmaf(gxk, yk, rs[k]);
+        r0[k] = fmaf(gr0, yk, r0[k]);
+        r1[k] = fmaf(gr1, yk, r1[k]);
+        r2[k] = fmaf(gr2, yk, r2[k]);
+        go.v[k] = __float2bfloat16_rn(p_dm[c + k] * gv);
+      }
+      *reinterpret_cast<V*>(g_out + ((int64_t)b * HW + p0 + pl) * C + c) = go;
+    }
+    __syncthreads();   // every thread is done with stage st before it is refilled (by the issue of iteration i+1)
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    atomicAdd(&red[0 * C + c + k], rs[k]);
+    atomicAdd(&red[1 * C + c + k], rd[k]);
+    atomicAdd(&red[2 * C + c + k], r0[k]);
+    atomicAdd(&red[3 * C + c + k], r1[k]);
+    atomicAdd(&red[4 * C + c + k], r2[k]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += 256) {
+    if (R_s != nullptr) atomicAdd(R_s + (int64_t)b * R_bs + i, red[i]);
+    if (R_d != nullptr) atomicAdd(R_d + (int64_t)b * R_bs + i, red[C + i]);
+    if (R_rgb != nullptr) {
+      atomicAdd(R_rgb + (int64_t)b * R_rgb_bs + i, red[2 * C + i]);
+      atomicAdd(R_rgb + (int64_t)b * R_rgb_bs + C + i, red[3 * C + i]);
+      atomicAdd(R_rgb + (int64_t)b * R_rgb_bs + 2 * C + i, red[4 * C + i]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // blur_bwd: g_t[u][v] = sum_{i,j} f[i] f[j] * g_v[u-i+1][v-j+1]  on the padded (TH x TW) grid of the
 // up-conv output; writes d * g_t and reduces R_d += g_t * t_saved.
 // ------------------------------------------------------------------------------------------------
@@ -290,6 +438,23 @@ int launch_act_bwd(void* g_out, const void* g_xn, const float* g_rgb, const void
                    const float* wr, int64_t wr_bs, const float* demod, int64_t demod_bs, const float* noise, int64_t noise_bs,
                    const float* noise_w, const float* bias, float* R_s, float* R_d, int64_t R_bs, float* R_rgb,
                    int64_t R_rgb_bs, int B, int HW, int C, cudaStream_t st) {
+  if (sizeof(T) == 2 && !g_switches.fir_simt && C >= 32 && C <= 512 && (C & (C - 1)) == 0) {
+    // 16 KB tiles: P = 8192 / C pixels; 16 tiles per CTA keep the double-buffered ring busy
+    const int P = kBwTileBytes / (C * 2);
+    const int ntiles = ceil_div(HW, P);
+    const int per_cta = std::min(ntiles, 16);
+    dim3 grid(ceil_div(ntiles, per_cta), B);
+    const size_t smem = 4 * kBwTileBytes + sizeof(float) * 11 * C;
+    static bool attr_set = false;
+    if (!attr_set) {
+      L2I_CUDA_TRY(cudaFuncSetAttribute(act_bwd_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kBwTileBytes + 4 * 11 * 512));
+      attr_set = true;
+    }
+    act_bwd_bulk_kernel<<<grid, 256, smem, st>>>((__nv_bfloat16*)g_out, (const __nv_bfloat16*)g_xn, g_rgb, (const __nv_bfloat16*)y, s_next,
+                                                 s_next_bs, wr, wr_bs, demod, demod_bs, noise, noise_bs, noise_w, bias, R_s, R_d, R_bs,
+                                                 R_rgb, R_rgb_bs, HW, C, per_cta);
+    return check_launch("act_bwd_bulk");
+  }
   constexpr int VEC = 4;   // 8-byte (bf16) / 16-byte (fp32) vectors: small register arrays leave room for 4 pixels in flight
   if (C % VEC != 0 || C / VEC > 256) { set_error("act_bwd: unsupported C=%d", C); return L2I_ERR_UNSUPPORTED; }
   const int chunk = std::max(256, std::min(HW, 4096));
