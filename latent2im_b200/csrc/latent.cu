@@ -61,7 +61,8 @@ int launch_linear(float* y, int64_t y_stride, const float* x, int64_t x_stride, 
 // [EqualLinear(D, D, lr_mul) + fused leaky relu].  One CTA per latent row keeps the activation vector in shared
 // memory between layers, so the 8 dependent layers cost one launch instead of 9; every warp produces D/16 outputs per
 // layer, four weight rows (16 independent 16-byte loads per lane) in flight at a time.  Weights stream from L2.
-constexpr int kMapThreads = 512;
+constexpr int kMapThreads = 1024;
+constexpr int kMapRows = 8;      // output rows per warp pass: 8 x 4 independent 16-byte weight loads per lane in flight
 __global__ void __launch_bounds__(kMapThreads)
 mapping_fused_kernel(float* __restrict__ w_out, const float* __restrict__ z, const float* const* __restrict__ Ws,
                      const float* const* __restrict__ bs, int n_mlp, int D, float wscale, float bscale) {
@@ -87,22 +88,25 @@ mapping_fused_kernel(float* __restrict__ w_out, const float* __restrict__ z, con
   for (int l = 0; l < n_mlp; ++l) {
     const float* W = Ws[l];
     const float* bias = bs[l];
-    for (int n0 = warp * 4; n0 < D; n0 += kWarps * 4) {   // 4 output rows per pass (D % 4 == 0)
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int n0 = warp * kMapRows; n0 < D; n0 += kWarps * kMapRows) {   // kMapRows output rows per pass (rows past D are skipped)
+      float acc[kMapRows];
+#pragma unroll
+      for (int r = 0; r < kMapRows; ++r) acc[r] = 0.f;
       for (int k4 = lane; k4 < D4; k4 += 32) {
         const float4 xv = *reinterpret_cast<const float4*>(cur + 4 * k4);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const float4 wv = __ldg(reinterpret_cast<const float4*>(W + (int64_t)(n0 + r) * D) + k4);
+        for (int r = 0; r < kMapRows; ++r) {
+          const int n = min(n0 + r, D - 1);
+          const float4 wv = __ldg(reinterpret_cast<const float4*>(W + (int64_t)n * D) + k4);
           acc[r] = fmaf(wv.x, xv.x, fmaf(wv.y, xv.y, fmaf(wv.z, xv.z, fmaf(wv.w, xv.w, acc[r]))));
         }
       }
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
+      for (int r = 0; r < kMapRows; ++r) {
         float v = acc[r];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-        if (lane == 0) {
+        if (lane == 0 && n0 + r < D) {
           v = v * wscale + bias[n0 + r] * bscale;
           nxt[n0 + r] = lrelu(v, 0.2f) * 1.4142135623730951f;
         }
