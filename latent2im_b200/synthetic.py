@@ -14,9 +14,14 @@ import numpy as np
 import torch
 
 
-def synthetic_state_dict(shapes: dict, seed: int = 0, lr_mlp: float = 0.01) -> dict:
+def synthetic_state_dict(shapes: dict, seed: int = 0, lr_mlp: float = 0.01, rgb_gain: float = 1.0) -> dict:
     """``shapes``: key -> shape (from any Generator's ``state_dict()``).  FIR kernels
-    (``*.kernel``) are left out - they are constants of the architecture."""
+    (``*.kernel``) are left out - they are constants of the architecture.
+
+    ``rgb_gain`` scales the ToRGB conv weights and biases.  With the unit-variance recipe (1.0, the one the golden
+    fixtures were generated with) a random-init generator emits images spanning about +-7, seven times the [-1, 1]
+    range of a trained one; 0.25 brings the synthetic images into that range, which is what an absolute
+    (peak-to-peak 2) PSNR gate presumes."""
     g = torch.Generator(device="cpu").manual_seed(seed)
     out = {}
     for key in sorted(shapes):
@@ -32,18 +37,22 @@ def synthetic_state_dict(shapes: dict, seed: int = 0, lr_mlp: float = 0.01) -> d
             v = 1.0 + 0.1 * r                   # bias_init = 1
         elif key.endswith(".noise.weight"):
             v = 0.1 * r
-        elif key.endswith(".activate.bias") or (key.endswith(".bias") and "to_rgb" in key):
+        elif key.endswith(".bias") and "to_rgb" in key:
+            v = 0.1 * r * rgb_gain
+        elif key.endswith(".activate.bias"):
             v = 0.1 * r
+        elif "to_rgb" in key and key.endswith(".conv.weight"):
+            v = r * rgb_gain
         else:                                   # conv / modulation / const input / noise buffers
             v = r
         out[key] = v
     return out
 
 
-def load_synthetic(generator, seed: int = 0):
+def load_synthetic(generator, seed: int = 0, rgb_gain: float = 1.0):
     """Overwrites ``generator``'s parameters and noise buffers in place with the synthetic recipe."""
     sd = generator.state_dict()
-    syn = synthetic_state_dict({k: v.shape for k, v in sd.items()}, seed, getattr(generator, "lr_mlp", 0.01))
+    syn = synthetic_state_dict({k: v.shape for k, v in sd.items()}, seed, getattr(generator, "lr_mlp", 0.01), rgb_gain)
     with torch.no_grad():
         for k, v in syn.items():
             sd[k].copy_(v.to(sd[k].device))
