@@ -393,12 +393,18 @@ class TransformGraph:
         return np.uint8(np.clip(((ims + 1) / 2.0) * 255, 0, 255))
 
     def apply_alpha(self, graph_inputs, alpha_to_graph, layers=None, name=None, trainEmbed=False, index_=None,
-                    given_w=None, return_uint8=False):
+                    given_w=None, return_uint8=False, cached_original=None):
+        """``cached_original`` = (latent_w, out_zs, alpha_org) of an earlier call on the same z: the reference recomputes
+        G(w) and R(G(w)) for every panel of a sweep (transform_base.py:554-603 inside the loop of :606-659); passing the
+        first panel's result skips G-forward #1 and the regressor for the others."""
         with torch.no_grad():
             zs = graph_inputs["z"]
-            latent_w = given_w if given_w is not None else self.get_w(zs)
-            out_zs = self.get_logits({"w": latent_w})
-            alpha_org = self.get_reg_preds(out_zs)
+            if cached_original is not None:
+                latent_w, out_zs, alpha_org = cached_original
+            else:
+                latent_w = given_w if given_w is not None else self.get_w(zs)
+                out_zs = self.get_logits({"w": latent_w})
+                alpha_org = self.get_reg_preds(out_zs)
             target = torch.as_tensor(np.asarray(alpha_to_graph), dtype=torch.float32, device=self.device)
             alpha_delta = self.get_alphas(alpha_org, target)
             if index_ is not None:
@@ -406,17 +412,22 @@ class TransformGraph:
                 alpha_delta[:, col] = target[:, 0] - alpha_org[:, col]
             latent_w_new = self.get_w_new_tensor(latent_w, alpha_delta, layers=layers, name=name, index_=index_)
             best_im_out = self.get_logits({"w": latent_w_new})
+        self._last_original = (latent_w, out_zs, alpha_org)
         return best_im_out, alpha_org, out_zs
 
     def vis_multi_image_batch_alphas(self, graph_inputs, filename, alphas_to_graph, alphas_to_target, batch_start,
                                      layers=None, name=None, wgt=False, wmask=False, trainEmbed=False, computeL2=False,
-                                     given_w=None, index_=None):
+                                     given_w=None, index_=None, cache_original=False):
         from latent2im_b200.utils import image
         zs_batch = graph_inputs["z"]
         panels = []
+        cached = None
         for ag, _ in zip(alphas_to_graph, alphas_to_target):
             z = torch.Tensor(zs_batch).to(self.device)
-            im, alpha_org, _ = self.apply_alpha({"z": z}, ag, name=name, layers=layers, given_w=given_w, index_=index_)
+            im, alpha_org, _ = self.apply_alpha({"z": z}, ag, name=name, layers=layers, given_w=given_w, index_=index_,
+                                                cached_original=cached)
+            if cache_original:
+                cached = self._last_original
             u8 = torch.empty(im.shape[0], im.shape[2], im.shape[3], 3, device=im.device, dtype=torch.uint8)
             nt.check(nt.load().l2i_image_to_uint8(u8.data_ptr(), im.contiguous().data_ptr(), im.shape[0], im.shape[2],
                                                   im.shape[3], nt.stream_ptr(im.device)), "image_to_uint8")

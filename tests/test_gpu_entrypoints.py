@@ -29,3 +29,6 @@ def test_train_then_vis_round_trip(tmp_path, monkeypatch):
     import PIL.Image
     im = PIL.Image.open(pngs[0])
     assert im.size == (4 * 33 + 1, 34)     # 4 panels of 32 px with 1 px padding
+    img_dir2 = vis_w.main([os.path.join(out, "opt.yml"), "--save_path_w", ckpt, "--noise_seed", "0", "--num_samples", "2",
+                           "--num_panels", "3", "--cache_original", "--output_dir", str(tmp_path / "cached")])
+    assert len(glob.glob(os.path.join(img_dir2, "*.png"))) == 2

@@ -31,6 +31,8 @@ def main(argv=None):
     v.parser.add_argument("--updateGAN", action="store_true")
     v.parser.add_argument("--size", type=int, default=None)
     v.parser.add_argument("--batch_size", type=int, default=None)
+    v.parser.add_argument("--cache_original", action="store_true",
+                          help="compute G(w) and R(G(w)) once per batch instead of once per panel (the reference recomputes them)")
     opt, conf = v.parse(argv)
     assert torch.cuda.is_available(), "vis_w.py needs a CUDA device (there is no CPU fallback)"
     if opt.gpu:
@@ -63,7 +65,7 @@ def main(argv=None):
                                                 min_alpha=opt.min_alpha, wgt=True)
         g.vis_multi_image_batch_alphas(batch, filename, alphas_to_graph=to_graph, alphas_to_target=to_target, layers=layers,
                                        batch_start=s.start, name=name, wgt=False, wmask=False, trainEmbed=opt.trainEmbed,
-                                       computeL2=False, given_w=None)
+                                       computeL2=False, given_w=None, cache_original=opt.cache_original)
     html.make_html(out_dir)
     return out_dir
 
