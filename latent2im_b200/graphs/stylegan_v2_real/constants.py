@@ -20,3 +20,5 @@ g_path = os.environ.get("L2I_G_PATH", "/path/550000.pt")
 allow_random_init = True
 compute_dtype = "fp32" if os.environ.get("L2I_DTYPE", "bf16").lower() in ("fp32", "f32", "float32") else "bf16"
 walk_is_mlp = False
+# stock ResNet-50 regressor under bf16 autocast + channels_last (train.py --amp); False = the reference's fp32 arithmetic
+reg_amp = os.environ.get("L2I_REG_AMP", "0") not in ("0", "")

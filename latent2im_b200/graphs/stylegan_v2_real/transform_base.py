@@ -324,6 +324,8 @@ class TransformGraph:
         elif not getattr(constants, "allow_random_init", True):
             raise FileNotFoundError(constants.reg_path)
         model = model.to(self.device).eval()
+        if getattr(constants, "reg_amp", False):
+            model = model.to(memory_format=torch.channels_last)
         for p in model.parameters():
             p.requires_grad_(False)  # frozen: only data gradients flow through R
         return model, None
@@ -353,8 +355,17 @@ class TransformGraph:
             layers = [int(i) for i in layers]
         return self.walk(multi_ws, alpha=alpha, layers=layers)
 
+    def _regress(self, logit):
+        """The attribute regressor is a stock torchvision ResNet-50 (outside the accelerated path).  With
+        ``constants.reg_amp`` it runs channels-last under bf16 autocast (about 2x faster at 1024 px); default = the
+        reference's fp32 NCHW arithmetic."""
+        if getattr(constants, "reg_amp", False):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return self.regressor(logit.contiguous(memory_format=torch.channels_last)).float()
+        return self.regressor(logit)
+
     def get_reg_preds(self, logit):
-        preds = self.regressor(logit)[:, self.attrIdx]
+        preds = self._regress(logit)[:, self.attrIdx]
         return preds.unsqueeze(1) if preds.ndim == 1 else preds
 
     def get_alphas(self, alpha_org, alpha_target):
@@ -364,7 +375,7 @@ class TransformGraph:
         return -(y * pred.clamp(min=eps).log() + (1 - y) * (1 - pred).clamp(min=eps).log()).mean()
 
     def get_reg_loss(self, feed_dict):
-        preds = self.regressor(feed_dict["logit"])[:, self.attrIdx]
+        preds = self._regress(feed_dict["logit"])[:, self.attrIdx]
         return self.get_bce_loss(preds, feed_dict["alpha"].to(torch.double)).mean()
 
     def optimizeParametersAll(self, feed_dict, trainEmbed, updateGAN, no_content_loss=False, no_gan_loss=False):

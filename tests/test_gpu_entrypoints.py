@@ -29,6 +29,11 @@ def test_train_then_vis_round_trip(tmp_path, monkeypatch):
     import PIL.Image
     im = PIL.Image.open(pngs[0])
     assert im.size == (4 * 33 + 1, 34)     # 4 panels of 32 px with 1 px padding
+    out_amp = train.main(["--model", "stylegan_v2_real", "--transform", "face", "--num_samples", "4", "--learning_rate", "1e-3",
+                          "--latent", "w", "--walk_type", "linear", "--loss", "l2", "--attrList", "Smiling", "--attrPath", attr,
+                          "--models_dir", str(tmp_path / "amp"), "--overwrite_config", "--no_gan_loss", "--no_content_loss",
+                          "--size", "32", "--batch_size", "2", "--dtype", "bf16", "--epochs", "1", "--max_iters", "1", "--amp"])
+    assert os.path.exists(os.path.join(out_amp, "model_w_1_final_walk_module.ckpt"))
     img_dir2 = vis_w.main([os.path.join(out, "opt.yml"), "--save_path_w", ckpt, "--noise_seed", "0", "--num_samples", "2",
                            "--num_panels", "3", "--cache_original", "--output_dir", str(tmp_path / "cached")])
     assert len(glob.glob(os.path.join(img_dir2, "*.png"))) == 2

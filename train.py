@@ -32,6 +32,7 @@ def main(argv=None):
     t = TrainOptions()
     t.initialize()
     t.parser.add_argument("--log_every", type=int, default=10)
+    t.parser.add_argument("--amp", action="store_true", help="run the stock ResNet-50 regressor under bf16 autocast + channels_last")
     rank, world, local = parallel.world_info()
     opt = t.parse(argv, print_opt=(rank == 0))
     assert torch.cuda.is_available(), "train.py needs a CUDA device (there is no CPU fallback)"
@@ -51,6 +52,8 @@ def main(argv=None):
     if opt.dtype:
         constants.compute_dtype = opt.dtype
     constants.walk_is_mlp = bool(opt.walk_mlp)
+    if opt.amp:
+        constants.reg_amp = True
 
     kw = util.set_graph_kwargs(opt)
     g = graphs.find_model_using_name(opt.model, opt.transform)(**kw)
