@@ -308,3 +308,21 @@ def test_fallback_kernel_paths_stay_correct(env, monkeypatch):
         gen.set_native(dtype=dt)
         out[dt], _ = gen(lat, input_is_latent=True, noise=noise)
     assert _psnr(out[torch.bfloat16].double(), out[torch.float32].double()) >= 45.0
+
+
+def test_large_batch_matches_single_sample_runs():
+    """Samples are independent: image i of a 40-latent batch at 1024 px (activation tensors > 2^31 bytes, the
+    reference's int32 indexing territory) equals the image of the same latent run alone - bit for bit."""
+    from latent2im_b200.graphs.stylegan_v2_real.networks import Generator
+    size, batch = 1024, 40
+    gen = load_synthetic(Generator(size, 512, 2), seed=1, rgb_gain=0.25).cuda()
+    gen.set_native(dtype=torch.bfloat16, max_batch=batch)
+    z = torch.tensor(synthetic_z(batch, 3), dtype=torch.float32).cuda()
+    lat = gen.style(z)[:, None, :].repeat(1, gen.n_latent, 1)
+    noise = [n.cuda() for n in synthetic_noise(gen.num_layers, batch)]
+    with torch.no_grad():
+        big, _ = gen(lat, input_is_latent=True, noise=noise)
+        for i in (0, 17, batch - 1):
+            one, _ = gen(lat[i:i + 1], input_is_latent=True, noise=[n[i:i + 1] for n in noise])
+            assert torch.equal(one[0], big[i]), i
+    assert torch.isfinite(big).all()
