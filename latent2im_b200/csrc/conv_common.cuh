@@ -72,7 +72,8 @@ struct EpiParams {
   int fused_skip;           // 1: write skip_out directly (requires a single N tile)
   const float* rgb_bias;    // [3]
   const float* skip_in;     // [B][3][H/2][W/2] or nullptr
-  float* skip_out;          // [B][3][H][W]
+  float* skip_out;          // [B][3][H][W]; may be nullptr when only image_u8 is wanted (2x2-block kernel)
+  uint8_t* image_u8;        // optional fused output of the LAST ToRGB: [B][H][W][3] = clip((x+1)/2*255) truncated (transform_base.py:625-626)
   float fir[4];             // separable up-sampling taps (already * factor), flipped order
 };
 

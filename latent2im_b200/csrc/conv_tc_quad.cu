@@ -305,11 +305,32 @@ conv_tc_quad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
       if (e.wr != nullptr && ok) {
         float* dst = e.fused_skip ? e.skip_out : e.rgb_part;
+        if (dst != nullptr) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          float* pl = dst + ((int64_t)b * 3 + c) * plane + (int64_t)Y * p.W + X;
-          *reinterpret_cast<float2*>(pl) = make_float2(rgb[0][c] + up[0][c], rgb[1][c] + up[1][c]);
-          *reinterpret_cast<float2*>(pl + p.W) = make_float2(rgb[2][c] + up[2][c], rgb[3][c] + up[3][c]);
+          for (int c = 0; c < 3; ++c) {
+            float* pl = dst + ((int64_t)b * 3 + c) * plane + (int64_t)Y * p.W + X;
+            *reinterpret_cast<float2*>(pl) = make_float2(rgb[0][c] + up[0][c], rgb[1][c] + up[1][c]);
+            *reinterpret_cast<float2*>(pl + p.W) = make_float2(rgb[2][c] + up[2][c], rgb[3][c] + up[3][c]);
+          }
+        }
+        if (e.image_u8 != nullptr) {
+          // final image as uint8 NHWC, same fp32 arithmetic as image_to_uint8_kernel: the two pixels of a row are 6 contiguous bytes
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            uint8_t q8[6];
+#pragma unroll
+            for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                float v = ((rgb[a * 2 + bb][c] + up[a * 2 + bb][c] + 1.0f) / 2.0f) * 255.0f;
+                v = fminf(fmaxf(v, 0.f), 255.f);
+                q8[bb * 3 + c] = (uint8_t)v;
+              }
+            uint16_t* o = reinterpret_cast<uint16_t*>(e.image_u8 + (((int64_t)b * p.H + Y + a) * p.W + X) * 3);   // X even: 2-byte aligned
+            o[0] = (uint16_t)(q8[0] | (q8[1] << 8));
+            o[1] = (uint16_t)(q8[2] | (q8[3] << 8));
+            o[2] = (uint16_t)(q8[4] | (q8[5] << 8));
+          }
         }
       }
     }

@@ -517,6 +517,13 @@ extern "C" int l2i_generator_forward(l2i_generator_t* g, const float* latent, in
     const bool final_rgb = rgb_i + 1 == g->rgbs.size();
     float* skip_dst = (final_rgb && image != nullptr) ? image : g->skip[skip_sel];
     e.skip_out = skip_dst;
+    // last layer on the 2x2-block kernel with only the uint8 image wanted: the cast is fused into its epilogue
+    bool fused_u8 = false;
+    if (final_rgb && image == nullptr && image_u8 != nullptr && !keep && !f32 && layer_uses_quad(g, L, B)) {
+      e.image_u8 = image_u8;
+      e.skip_out = nullptr;
+      fused_u8 = true;
+    }
     e.rgb_part = g->rgb_part;
     const int n_tile = (f32 || g->conv_impl == 1 || !conv_tc_supported(geom, e)) ? 64 : conv_tc_block_n(geom);
     const int nparts = ceil_div(L.cout, n_tile);
@@ -533,12 +540,12 @@ extern "C" int l2i_generator_forward(l2i_generator_t* g, const float* latent, in
     }
     if (s_next) cur ^= 1;
     g->conv_out[li] = s_next ? g->act[cur] : nullptr;
-    g->skip_out[rgb_i] = skip_dst;
-    skip_prev = skip_dst;
+    g->skip_out[rgb_i] = fused_u8 ? nullptr : skip_dst;
+    skip_prev = fused_u8 ? nullptr : skip_dst;
     skip_sel ^= 1;
     ++rgb_i;
   }
-  if (image_u8 != nullptr) {
+  if (image_u8 != nullptr && skip_prev != nullptr) {
     auto* sg_u = g->seg_begin("image_to_uint8", 2, 0.0, (double)B * g->size * g->size * 15.0, st);
     L2I_TRY(l2i_image_to_uint8(image_u8, skip_prev, B, g->size, g->size, stream));
     g->seg_end(sg_u, st);

@@ -326,3 +326,19 @@ def test_large_batch_matches_single_sample_runs():
             one, _ = gen(lat[i:i + 1], input_is_latent=True, noise=[n[i:i + 1] for n in noise])
             assert torch.equal(one[0], big[i]), i
     assert torch.isfinite(big).all()
+
+
+def test_fused_uint8_epilogue_of_the_last_layer_matches_the_separate_cast():
+    """uint8-only output at 1024 px comes straight from the 2x2-block kernel's epilogue; it must equal the separate
+    l2i_image_to_uint8 pass over the fp32 image (both are clip((x+1)/2*255) truncated, transform_base.py:625-626)."""
+    from latent2im_b200.graphs.stylegan_v2_real.networks import Generator
+    gen = load_synthetic(Generator(1024, 512, 2), seed=2, rgb_gain=0.25).cuda()
+    gen.set_native(dtype=torch.bfloat16, max_batch=2)
+    z = torch.tensor(synthetic_z(2, 5), dtype=torch.float32).cuda()
+    lat = gen.style(z)[:, None, :].repeat(1, gen.n_latent, 1)
+    noise = [n.cuda() for n in synthetic_noise(gen.num_layers, 2)]
+    with torch.no_grad():
+        img, u8_sep = gen.synthesize(lat, noise=noise, want_uint8=True, want_float=True)
+        u8_fused = gen.synthesize(lat, noise=noise, want_uint8=True, want_float=False)
+    assert torch.equal(u8_sep, u8_fused)
+    assert torch.equal(u8_sep, clip_to_uint8_ref(img.cpu()).permute(0, 2, 3, 1).cuda())
