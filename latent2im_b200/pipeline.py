@@ -7,7 +7,9 @@ i.e. the body of the reference's ``apply_alpha`` + the host-side ``clip((x+1)/2*
 factored out (``alpha`` is the walk step epsilon).  Host buffers are
 pinned once; every call copies z / alpha to the device on the current stream and the uint8 result
 back on a dedicated copy stream (double-buffered), so the 3 MB/image device->host transfer of step i
-overlaps the kernels of step i+1.
+overlaps the kernels of step i+1.  The per-layer noise of call i+1 (17 Philox launches, 358 MB at 1024 px x 32) is drawn
+on a side stream while call i's convolutions run: same generator, same draw order and shapes as
+``NoiseInjection`` (networks.py:281-286), so a seeded run still consumes the reference's random stream.
 """
 from __future__ import annotations
 
@@ -27,6 +29,9 @@ class EditPipeline:
         self.out_hosts = [torch.empty(batch, size, size, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
         self.out_devs = [torch.empty(batch, size, size, 3, dtype=torch.uint8, device=self.device) for _ in range(2)]
         self.copy_stream = torch.cuda.Stream(self.device)
+        self.noise_stream = torch.cuda.Stream(self.device)
+        self._next_noise = None            # (tensors, ready event) drawn ahead for the next call
+        self._noise_in_use = None
         self.copy_done = [None, None]      # event: device->host copy out of buffer k has finished
         self._k = 0
         self.z_dev = torch.empty(batch, dim, dtype=torch.float32, device=self.device)
@@ -41,6 +46,28 @@ class EditPipeline:
     def d2h_bytes(self) -> int:
         return self.out_hosts[0].numel()
 
+    def _draw_noise_ahead(self, batch):
+        with torch.cuda.stream(self.noise_stream):
+            nz = [torch.empty(batch, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2), device=self.device, dtype=torch.float32).normal_()
+                  for i in range(self.gen.num_layers)]
+            ev = torch.cuda.Event()
+            ev.record(self.noise_stream)
+        return nz, ev
+
+    def _take_noise(self, batch):
+        """Fresh per-layer noise for this call (drawn ahead on the side stream when a previous call left one) and the
+        draw for the next call started behind it."""
+        main = torch.cuda.current_stream(self.device)
+        if self._next_noise is None or self._next_noise[0][0].shape[0] != batch:
+            self._next_noise = self._draw_noise_ahead(batch)
+        nz, ev = self._next_noise
+        main.wait_event(ev)
+        for t in nz:
+            t.record_stream(main)          # allocated on the side stream, consumed by kernels on the main stream
+        self._noise_in_use = nz
+        self._next_noise = None
+        return nz
+
     @torch.no_grad()
     def edit_device(self, z_dev, alpha_dev, layers=None, noise=None, want_uint8=False, out_uint8=None):
         """Device-resident part: mapping -> walk -> synthesis.  Returns the fp32 image (reference
@@ -48,7 +75,13 @@ class EditPipeline:
         w = self.gen.style(z_dev)
         ws = self.walk([w] * self.gen.n_latent, alpha_dev, layers=layers)
         latent = torch.stack(ws, 1) if not _is_block(ws) else ws[0]._base
-        return self.gen.synthesize(latent, noise=noise, want_uint8=want_uint8, want_float=not want_uint8, out_uint8=out_uint8)
+        drew = noise is None
+        if drew:
+            noise = self._take_noise(latent.shape[0])
+        out = self.gen.synthesize(latent, noise=noise, want_uint8=want_uint8, want_float=not want_uint8, out_uint8=out_uint8)
+        if drew:   # the next call's noise is generated while the kernels just enqueued run
+            self._next_noise = self._draw_noise_ahead(latent.shape[0])
+        return out
 
     @torch.no_grad()
     def edit(self, z, alpha, layers=None, noise=None, sync=True) -> np.ndarray:

@@ -75,3 +75,22 @@ def test_pipeline_needs_cuda():
     from latent2im_b200.pipeline import EditPipeline
     with pytest.raises(RuntimeError):
         EditPipeline(Generator(16, 32, 1), None, 2, device=torch.device("cpu"))
+
+
+def test_noise_drawn_ahead_consumes_the_reference_stream():
+    """EditPipeline draws call i+1's noise on a side stream during call i; a seeded run must still see exactly the
+    tensors ``NoiseInjection`` would draw (same generator, order, shapes) - checked against explicit-noise runs."""
+    spec, sd, w0, pipe = _setup(16, 32, 1, 2, torch.float32)
+    z = torch.tensor(synthetic_z(2, 1, 32), dtype=torch.float32).cuda()
+    alpha = torch.full((2, 1), 0.3, device="cuda")
+    torch.manual_seed(77)
+    pipe._next_noise = None
+    a1 = pipe.edit_device(z, alpha).clone()
+    a2 = pipe.edit_device(z, alpha).clone()
+    torch.manual_seed(77)
+    draws = [[torch.empty(2, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2), device="cuda").normal_() for i in range(spec.num_layers)]
+             for _ in range(3)]
+    pipe._next_noise = None
+    b1 = pipe.edit_device(z, alpha, noise=draws[0])
+    b2 = pipe.edit_device(z, alpha, noise=draws[1])
+    assert torch.equal(a1, b1) and torch.equal(a2, b2) and not torch.equal(a1, a2)
