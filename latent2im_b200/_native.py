@@ -15,7 +15,8 @@ import torch
 F32, BF16, F16 = 0, 1, 2
 _DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libl2i_b200.so")
+# L2I_LIB: debug override (A/B runs of differently compiled builds); the default is the in-tree build
+_LIB_PATH = os.environ.get("L2I_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libl2i_b200.so")
 _lib: Optional[C.CDLL] = None
 
 _vp, _i64, _i32, _f32, _u64 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_uint64

@@ -12,6 +12,11 @@
 // (overlapping UMMA descriptors); r = 0 and r = 3 are N = 64 MMAs into the lower / upper half of the accumulator.
 // A comes straight from the NHWC halo tile (TMA, once per output tile): GEMM rows of one 8-row group are 8 adjacent
 // pixels (128 B apart), groups are two image rows apart (stride-byte-offset = 2 x halo pitch).
+//
+// The layer is epilogue-bound (demod, noise, bias, leaky-relu, ToRGB and the skip up-sampling for 256 pixels x 64
+// channels per tile), so the epilogue issues no global gathers: warp 3 TMA-loads the tile's noise patch (32 x 8 fp32)
+// and low-resolution skip patch (3 x 18 x 12 fp32, out-of-image samples zero-filled = upfirdn2d's zero padding) into a
+// six-deep ring, two tiles ahead of each epilogue warpgroup, and the MMA issuer has four accumulators to run ahead in.
 #include "tc_epilogue.cuh"
 
 namespace l2i {
@@ -25,6 +30,12 @@ constexpr int kVHaloBytes = kVW * kVH * 128;               // 43520
 constexpr int kVStageBytes = (kVHaloBytes + 1023) & ~1023;
 constexpr int kVStages = 2;
 constexpr int kVGroups = 3;                               // 512 threads -> 128 registers per thread
+constexpr int kVAccs = 4;                                 // accumulators of 128 TMEM columns
+constexpr int kVPatches = 2 * kVGroups;                   // noise / skip patch ring (tile it -> buffer it % 6, always the same warpgroup)
+constexpr int kVSkipW = 12, kVSkipH = 18;                 // low-res skip patch: columns n0-4 .. n0+7 (16-byte aligned start), rows m0-1 .. m0+16
+constexpr int kVSkipFloats = 3 * kVSkipH * kVSkipW;       // 648
+constexpr int kVSkipStride = (kVSkipFloats + 31) & ~31;   // 672 floats: buffers stay 128-byte aligned
+constexpr int kVNoiseFloats = 32 * 8;                     // the tile's 32 rows x 8 columns
 constexpr int kVThreads = 128 + kVGroups * 128;
 constexpr int kVWBytes = 9 * 64 * 128;                     // 73728: nine 64 x 64 bf16 tiles
 constexpr int kVStageOutBytes = 2048;                      // per epilogue warp: 32 pixels x 32 channels, SWIZZLE_64B (TMA store source)
@@ -36,6 +47,8 @@ struct VPairParams {
   int tiles_x, tiles_y, total_tiles;
   uint32_t idesc128, idesc64;
   int tma_store;             // activation output goes through per-warp staging tiles + strided TMA tensor stores
+  int has_skip, has_noise;   // tmap_s / tmap_n are valid: warp 3 loads the patches of every tile
+  int noise_per_sample;      // 0: one noise image broadcast over the batch
   EpiParams e;
 };
 
@@ -54,7 +67,8 @@ __device__ __forceinline__ void vp_group_sync(int group) {
 
 __global__ void __launch_bounds__(kVThreads, 1)
 conv_tc_vpair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                     const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ VPairParams p) {
+                     const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_s,
+                     const __grid_constant__ CUtensorMap tmap_n, const __grid_constant__ VPairParams p) {
   constexpr int N = 128, CO = 64;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -63,9 +77,13 @@ conv_tc_vpair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   __shared__ __align__(16) float epi_smem[kVGroups * 6 * CO];
   __shared__ __align__(8) uint64_t full_bar[kVStages];
   __shared__ __align__(8) uint64_t empty_bar[kVStages];
-  __shared__ __align__(8) uint64_t tmem_full[kVGroups];
-  __shared__ __align__(8) uint64_t tmem_empty[kVGroups];
+  __shared__ __align__(8) uint64_t tmem_full[kVAccs];
+  __shared__ __align__(8) uint64_t tmem_empty[kVAccs];
+  __shared__ __align__(8) uint64_t patch_full[kVPatches];
+  __shared__ __align__(8) uint64_t patch_empty[kVPatches];
   __shared__ __align__(8) uint64_t w_bar;
+  __shared__ __align__(128) float skip_smem[kVPatches * kVSkipStride];
+  __shared__ __align__(128) float noise_smem[kVPatches * kVNoiseFloats];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -73,10 +91,13 @@ conv_tc_vpair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_w);
     if (p.tma_store) prefetch_tmap(&tmap_o);
+    if (p.has_skip) prefetch_tmap(&tmap_s);
+    if (p.has_noise) prefetch_tmap(&tmap_n);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kVStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < kVGroups; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+    for (int a = 0; a < kVAccs; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+    for (int a = 0; a < kVPatches; ++a) { mbar_init(&patch_full[a], 1); mbar_init(&patch_empty[a], 128); }
     mbar_init(&w_bar, 1);
     fence_barrier_init();
   }
@@ -110,20 +131,36 @@ conv_tc_vpair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         if (++stage == kVStages) { stage = 0; phase_bit ^= 1; }
       }
     }
+  } else if (warp == 3) {
+    // ===================== patch producer: the tile's noise and low-res skip boxes, up to six tiles ahead ========
+    if (lane == 0 && (p.has_skip || p.has_noise)) {
+      int buf = 0;
+      uint32_t buf_phase = 0;
+      const uint32_t bytes = (p.has_skip ? kVSkipFloats * 4u : 0u) + (p.has_noise ? kVNoiseFloats * 4u : 0u);
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int x0, y0, b;
+        decode(tile, x0, y0, b);
+        mbar_wait(&patch_empty[buf], buf_phase ^ 1);   // the epilogue that used this buffer six tiles ago has read it
+        mbar_expect_tx(&patch_full[buf], bytes);
+        if (p.has_skip) tma_load_4d(skip_smem + buf * kVSkipStride, &tmap_s, &patch_full[buf], (x0 >> 1) - 4, (y0 >> 1) - 1, 0, b);
+        if (p.has_noise) tma_load_3d(noise_smem + buf * kVNoiseFloats, &tmap_n, &patch_full[buf], x0, y0, p.noise_per_sample ? b : 0);
+        if (++buf == kVPatches) { buf = 0; buf_phase ^= 1; }
+      }
+    }
   } else if (warp == 1) {
     // ===================== MMA issuer: 48 MMAs per tile, no barrier inside a tile =====================
     if (lane == 0) {
       mbar_wait(&w_bar, 0);
       tc_fence_after();
       const uint32_t w_base = smem_u32(smem_w);
-      int stage = 0, grp = 0;
-      uint32_t phase_bit = 0, grp_phase = 0;
+      int stage = 0, acc = 0;
+      uint32_t phase_bit = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty[grp], grp_phase ^ 1);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         mbar_wait(&full_bar[stage], phase_bit);
         tc_fence_after();
         const uint32_t a_base = smem_u32(smem + stage * kVStageBytes);
-        const uint32_t tmem_d = tmem_base + (uint32_t)(grp * N);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * N);
         // input-row order 1, 2, 0, 3: the first MMA (r = 1, N = 128) initialises all 128 accumulator columns
 #pragma unroll
         for (int ri = 0; ri < 4; ++ri) {
@@ -143,9 +180,9 @@ conv_tc_vpair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           }
         }
         umma_commit(&empty_bar[stage]);
-        umma_commit(&tmem_full[grp]);
+        umma_commit(&tmem_full[acc]);
         if (++stage == kVStages) { stage = 0; phase_bit ^= 1; }
-        if (++grp == kVGroups) { grp = 0; grp_phase ^= 1; }
+        if (++acc == kVAccs) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
@@ -164,13 +201,13 @@ conv_tc_vpair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     const float nw = (e.noise != nullptr && e.noise_w != nullptr) ? __ldg(e.noise_w) * kSqrt2 : 0.f;
     const int64_t plane = (int64_t)p.H * p.W;
     const int lx = row & 7, lj = row >> 3;
-    uint32_t grp_phase = 0;
     int staged_b = -1;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      if (it % kVGroups != group) continue;
+    int it = group;
+    for (int tile = blockIdx.x + group * gridDim.x; tile < p.total_tiles; tile += kVGroups * gridDim.x, it += kVGroups) {
       int x0, y0, b;
       decode(tile, x0, y0, b);
+      const int acc = it & (kVAccs - 1), buf = it % kVPatches;
+      const uint32_t acc_parity = (uint32_t)(it / kVAccs) & 1u, buf_parity = (uint32_t)(it / kVPatches) & 1u;
       const int X = x0 + lx, Y = y0 + 2 * lj;              // upper pixel of the pair
       const bool ok = X < p.W && Y < p.H;                   // H is even: both pixels inside or both outside
 
@@ -188,30 +225,16 @@ conv_tc_vpair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       }
 
       float nzp[2] = {0.f, 0.f};
-      float up[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-      if (ok) {
-        if (e.noise != nullptr) {
-          const float* np = e.noise + (int64_t)b * e.noise_bs + (int64_t)Y * p.W + X;
-          nzp[0] = nw * __ldg(np);
-          nzp[1] = nw * __ldg(np + p.W);
-        }
-        if (e.fused_skip) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const float bias_c = __ldg(e.rgb_bias + c);
-            up[0][c] = up[1][c] = bias_c;
-            if (e.skip_in != nullptr) {
-              const float* pl = e.skip_in + ((int64_t)b * 3 + c) * (plane >> 2);
-              up[0][c] += upsample2x_at(pl, p.H >> 1, p.W >> 1, Y, X, e.fir);
-              up[1][c] += upsample2x_at(pl, p.H >> 1, p.W >> 1, Y + 1, X, e.fir);
-            }
-          }
-        }
+      if (p.has_skip || p.has_noise) mbar_wait(&patch_full[buf], buf_parity);
+      if (p.has_noise) {
+        const float* ns = noise_smem + buf * kVNoiseFloats + (2 * lj) * 8 + lx;
+        nzp[0] = nw * ns[0];
+        nzp[1] = nw * ns[8];
       }
 
-      mbar_wait(&tmem_full[group], grp_phase);
+      mbar_wait(&tmem_full[acc], acc_parity);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(group * N);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N);
       float rgb[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
       uint8_t* stage_tile = smem_stage_out + (warp - 4) * kVStageOutBytes;
       __nv_bfloat16* stage_row = (__nv_bfloat16*)stage_tile + lane * 32;     // this lane's 64-byte row of the staging tile
@@ -248,8 +271,30 @@ conv_tc_vpair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         }
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty[group]);
-      grp_phase ^= 1;
+      mbar_arrive(&tmem_empty[acc]);
+
+      // ---- ToRGB tail: bias + 2x FIR up-sampling of the skip image (ToRGB.forward, networks.py:349-358) from the patch.
+      // Output rows Y = 2m, 2m+1 read low-res rows m-1 (f0), m (f2) and m (f1), m+1 (f3); the column parity picks the taps.
+      float up[2][3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) up[0][c] = up[1][c] = e.fused_skip ? __ldg(e.rgb_bias + c) : 0.f;
+      if (p.has_skip) {
+        const int px = lx & 1;
+        const float wa = px ? e.fir[1] : e.fir[0], wb = px ? e.fir[3] : e.fir[2];
+        const float* sk = skip_smem + buf * kVSkipStride + lj * kVSkipW + (lx >> 1) + 3 + px;   // patch origin = (m0 - 1, n0 - 4)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float h[3];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const float* rowp = sk + (c * kVSkipH + i) * kVSkipW;
+            h[i] = fmaf(wa, rowp[0], wb * rowp[1]);
+          }
+          up[0][c] += fmaf(e.fir[0], h[0], e.fir[2] * h[1]);
+          up[1][c] += fmaf(e.fir[1], h[1], e.fir[3] * h[2]);
+        }
+      }
+      if (p.has_skip || p.has_noise) mbar_arrive(&patch_empty[buf]);   // patch values are in registers
 
       if (e.wr != nullptr && ok) {
         float* dst = e.fused_skip ? e.skip_out : e.rgb_part;
@@ -316,6 +361,27 @@ int launch_conv_tc_vpair(const void* in, const __nv_bfloat16* w, const ConvGeom&
     const uint32_t box[3] = {64, 64, 1};
     L2I_TRY(make_tmap(&tw, w, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
   }
+  CUtensorMap ts = ta, tn = ta;   // placeholders when there is no skip image / noise
+  p.has_skip = (e.fused_skip && e.skip_in != nullptr) ? 1 : 0;
+  if (p.has_skip) {
+    const uint64_t h2 = (uint64_t)g.H / 2, w2 = (uint64_t)g.W / 2;
+    const uint64_t dims[4] = {w2, h2, 3, (uint64_t)g.B};
+    const uint64_t str[4] = {4, w2 * 4, h2 * w2 * 4, 3 * h2 * w2 * 4};
+    const uint32_t box[4] = {kVSkipW, kVSkipH, 3, 1};
+    if ((uintptr_t)e.skip_in % 16 != 0 || (w2 * 4) % 16 != 0) { set_error("conv_tc_vpair: skip image must be 16-byte aligned"); return L2I_ERR_INVALID_ARG; }
+    L2I_TRY(make_tmap_f32(&ts, e.skip_in, 4, dims, str, box));
+  }
+  p.has_noise = (e.noise != nullptr && e.noise_w != nullptr) ? 1 : 0;
+  p.noise_per_sample = e.noise_bs != 0 ? 1 : 0;
+  if (p.has_noise) {
+    const uint64_t nb = p.noise_per_sample ? (uint64_t)g.B : 1;
+    const uint64_t bs = p.noise_per_sample ? (uint64_t)e.noise_bs * 4 : (uint64_t)g.H * g.W * 4;
+    const uint64_t dims[3] = {(uint64_t)g.W, (uint64_t)g.H, nb};
+    const uint64_t str[3] = {4, (uint64_t)g.W * 4, bs};
+    const uint32_t box[3] = {8, 32, 1};
+    if ((uintptr_t)e.noise % 16 != 0 || bs % 16 != 0) { set_error("conv_tc_vpair: noise must be 16-byte aligned"); return L2I_ERR_INVALID_ARG; }
+    L2I_TRY(make_tmap_f32(&tn, e.noise, 3, dims, str, box));
+  }
   CUtensorMap to = ta;
   p.tma_store = 0;
   if (e.out != nullptr && e.s_next != nullptr && e.y_out == nullptr && (uintptr_t)e.out % 16 == 0) {
@@ -337,7 +403,7 @@ int launch_conv_tc_vpair(const void* in, const __nv_bfloat16* w, const ConvGeom&
     attr_set = true;
   }
   const int grid = std::min(p.total_tiles, kNumSMs);
-  conv_tc_vpair_kernel<<<grid, kVThreads, kVSmem, st>>>(ta, tw, to, p);
+  conv_tc_vpair_kernel<<<grid, kVThreads, kVSmem, st>>>(ta, tw, to, ts, tn, p);
   return check_launch("conv_tc_vpair");
 }
 

@@ -30,8 +30,9 @@ class EditPipeline:
         self.out_devs = [torch.empty(batch, size, size, 3, dtype=torch.uint8, device=self.device) for _ in range(2)]
         self.copy_stream = torch.cuda.Stream(self.device)
         self.noise_stream = torch.cuda.Stream(self.device)
-        self._next_noise = None            # (tensors, ready event) drawn ahead for the next call
+        self._next_noise = None            # (tensors, ready event, set index) drawn ahead for the next call
         self._noise_in_use = None
+        self._noise_pool, self._noise_pool_batch, self._noise_free, self._noise_j = None, None, None, 0
         self.copy_done = [None, None]      # event: device->host copy out of buffer k has finished
         self._k = 0
         self.z_dev = torch.empty(batch, dim, dtype=torch.float32, device=self.device)
@@ -46,27 +47,50 @@ class EditPipeline:
     def d2h_bytes(self) -> int:
         return self.out_hosts[0].numel()
 
+    _NOISE_SETS = 3   # one in use by the kernels in flight, one drawn ahead, one spare for a host that runs ahead
+
+    def _noise_set(self, batch, j):
+        """Preallocated per-layer noise tensors of set ``j`` (no allocation in steady state: a host enqueueing many
+        steps ahead of the GPU would otherwise make the caching allocator cudaMalloc a fresh 11 MB/image set per step)."""
+        if self._noise_pool is None or self._noise_pool_batch != batch:
+            self._noise_pool = [[torch.empty(batch, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2), device=self.device, dtype=torch.float32)
+                                 for i in range(self.gen.num_layers)] for _ in range(self._NOISE_SETS)]
+            self._noise_free = [None] * self._NOISE_SETS   # event: the kernels that read set j have finished
+            self._noise_pool_batch, self._noise_j = batch, 0
+        return self._noise_pool[j]
+
     def _draw_noise_ahead(self, batch):
+        self._noise_set(batch, 0)
+        j = self._noise_j
+        self._noise_j = (j + 1) % self._NOISE_SETS
+        nz = self._noise_set(batch, j)
         with torch.cuda.stream(self.noise_stream):
-            nz = [torch.empty(batch, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2), device=self.device, dtype=torch.float32).normal_()
-                  for i in range(self.gen.num_layers)]
+            if self._noise_free[j] is not None:
+                self.noise_stream.wait_event(self._noise_free[j])
+            for t in nz:
+                t.normal_()
             ev = torch.cuda.Event()
             ev.record(self.noise_stream)
-        return nz, ev
+        return nz, ev, j
 
     def _take_noise(self, batch):
-        """Fresh per-layer noise for this call (drawn ahead on the side stream when a previous call left one) and the
-        draw for the next call started behind it."""
+        """Fresh per-layer noise for this call (drawn ahead on the side stream when a previous call left one); the
+        caller starts the draw for the next call behind the kernels it enqueues."""
         main = torch.cuda.current_stream(self.device)
         if self._next_noise is None or self._next_noise[0][0].shape[0] != batch:
+            self.noise_stream.wait_stream(main)    # a first draw must not overtake earlier work on the main stream
             self._next_noise = self._draw_noise_ahead(batch)
-        nz, ev = self._next_noise
+        nz, ev, j = self._next_noise
         main.wait_event(ev)
-        for t in nz:
-            t.record_stream(main)          # allocated on the side stream, consumed by kernels on the main stream
-        self._noise_in_use = nz
+        self._noise_in_use = j
         self._next_noise = None
         return nz
+
+    def _release_noise(self):
+        """Marks the set taken by the current call as free once the kernels enqueued so far have run."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._noise_free[self._noise_in_use] = ev
 
     @torch.no_grad()
     def edit_device(self, z_dev, alpha_dev, layers=None, noise=None, want_uint8=False, out_uint8=None):
@@ -80,6 +104,7 @@ class EditPipeline:
             noise = self._take_noise(latent.shape[0])
         out = self.gen.synthesize(latent, noise=noise, want_uint8=want_uint8, want_float=not want_uint8, out_uint8=out_uint8)
         if drew:   # the next call's noise is generated while the kernels just enqueued run
+            self._release_noise()
             self._next_noise = self._draw_noise_ahead(latent.shape[0])
         return out
 
