@@ -16,6 +16,8 @@ NUM_CHANNELS = 3
 reg_json = None
 reg_path = os.environ.get("L2I_REG_PATH", "/path/003_dict.model")
 g_path = os.environ.get("L2I_G_PATH", "/path/550000.pt")
+# torchvision vgg19 state_dict for the content loss (the reference downloads it: models.vgg19(pretrained=True))
+vgg_path = os.environ.get("L2I_VGG_PATH", "")
 # with no checkpoint on disk the modules keep their random initialisation (benchmarks, tests)
 allow_random_init = True
 compute_dtype = "fp32" if os.environ.get("L2I_DTYPE", "bf16").lower() in ("fp32", "f32", "float32") else "bf16"

@@ -408,3 +408,7 @@ class Generator(nn.Module):
             nt.check(h.lib.l2i_generator_read_activation(h.handle, name.encode(), out.data_ptr(), out.numel(), batch,
                                                          nt.stream_ptr(h.device)), "generator_read_activation")
         return out
+
+
+# the discriminator lives in its own module; re-exported under the reference's names
+from .discriminator import Discriminator, _ConvLayer as ConvLayer, _ResBlock as ResBlock  # noqa: E402,F401

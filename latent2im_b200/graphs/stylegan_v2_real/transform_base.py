@@ -15,7 +15,7 @@ Deviations from the shipped reference, all documented in DESIGN.md:
   ``walk(ws, alpha=..., layers=...)`` that ``get_w_new_tensor`` makes (TypeError as shipped);
 * G-forward #1 / R-forward #1 of the training step run without autograd (the branch contributes
   exactly zero to the walk gradient, SURVEY 3.2);
-* the discriminator and VGG19 loss terms are only built when their loss is requested.
+* the discriminator (own ops + cuDNN convs) and VGG19 (stock) loss terms are only built when their loss is requested.
 """
 import os
 
@@ -378,13 +378,72 @@ class TransformGraph:
         preds = self._regress(feed_dict["logit"])[:, self.attrIdx]
         return self.get_bce_loss(preds, feed_dict["alpha"].to(torch.double)).mean()
 
+    # ---- optional loss terms (built only when requested) -----------------
+    def get_discriminator(self):
+        """The reference's ``StyleGAN(lr).netD`` (stylegan2.py:21-29): a Discriminator at the generator's resolution,
+        never loaded from the checkpoint there; ``ckpt['d']`` is used here when the checkpoint file has one."""
+        if self.module.netD is None:
+            from .networks import Discriminator
+            d = Discriminator(constants.resolution)
+            if os.path.exists(constants.g_path):
+                ckpt = torch.load(constants.g_path, map_location="cpu", weights_only=False)
+                if "d" in ckpt:
+                    d.load_state_dict(ckpt["d"], strict=False)
+            d = d.to(self.device).eval()
+            for p in d.parameters():
+                p.requires_grad_(False)   # frozen: only the data gradient flows back to the walk
+            self.module.netD = d
+        return self.module.netD
+
+    def get_vgg_module(self):
+        """First eight modules of torchvision's VGG19 ``features`` = up to ``conv_4``, all the content loss reads
+        (transform_base.py:427-453, 536-538).  ``constants.vgg_path`` (a ``vgg19`` state_dict) replaces the reference's
+        ``pretrained=True`` download, which needs network."""
+        if getattr(self, "vgg19", None) is None:
+            import torchvision
+            full = torchvision.models.vgg19(weights=None)
+            path = getattr(constants, "vgg_path", "")
+            if path and os.path.exists(path):
+                full.load_state_dict(torch.load(path, map_location="cpu", weights_only=False))
+            elif not getattr(constants, "allow_random_init", True):
+                raise FileNotFoundError(path)
+            # out-of-place ReLUs: the conv outputs are loss operands (the reference swaps them too, transform_base.py:439-441)
+            vgg = torch.nn.Sequential(*[torch.nn.ReLU(inplace=False) if isinstance(m, torch.nn.ReLU) else m
+                                        for m in full.features[:8]]).to(self.device).eval()
+            for p in vgg.parameters():
+                p.requires_grad_(False)
+            self.vgg19 = vgg
+            self._vgg_mean = torch.tensor([0.485, 0.456, 0.406], device=self.device).view(-1, 1, 1)
+            self._vgg_std = torch.tensor([0.229, 0.224, 0.225], device=self.device).view(-1, 1, 1)
+        return self.vgg19
+
+    def get_content_loss(self, org_img, shifted_img):
+        """MSE between the VGG19 activations of the original and the edited image after conv_1 .. conv_4
+        (transform_base.py:427-453: the reference re-runs the growing prefix per layer; one pass gives the same values)."""
+        vgg = self.get_vgg_module()
+        a = (org_img.detach() - self._vgg_mean) / self._vgg_std
+        b = (shifted_img - self._vgg_mean) / self._vgg_std
+        losses = []
+        for layer in vgg:
+            a, b = layer(a), layer(b)
+            if isinstance(layer, torch.nn.Conv2d):
+                losses.append(torch.nn.functional.mse_loss(a.detach(), b))
+        return losses
+
     def optimizeParametersAll(self, feed_dict, trainEmbed, updateGAN, no_content_loss=False, no_gan_loss=False):
-        if not (no_content_loss and no_gan_loss):
-            raise NotImplementedError(
-                "the discriminator / VGG19 loss terms are outside the accelerated path (SURVEY section 2.1 rows 6, 8); "
-                "run with --no_content_loss --no_gan_loss")
+        """transform_base.py:455-487: ``reg`` alone, or ``10 reg + 0.05 content + 0.05 gan`` for the terms not disabled."""
         self.optimizers.zero_grad()
-        loss = self.get_reg_loss(feed_dict)
+        reg_loss = self.get_reg_loss(feed_dict)
+        if no_content_loss and no_gan_loss:
+            loss = reg_loss
+        else:
+            loss = 10 * reg_loss
+            if not no_content_loss:
+                content = self.get_content_loss(feed_dict["org"], feed_dict["logit"])
+                loss = loss + 0.05 * (sum(content) / len(content))
+            if not no_gan_loss:
+                d_fake = self.get_discriminator()(feed_dict["logit"])
+                loss = loss + 0.05 * torch.nn.functional.binary_cross_entropy_with_logits(d_fake, torch.ones_like(d_fake))
         loss.backward()
         # data parallel (one process per GPU): the only collective of the path, a no-op on a single GPU
         from latent2im_b200 import parallel

@@ -49,6 +49,18 @@ def synthetic_state_dict(shapes: dict, seed: int = 0, lr_mlp: float = 0.01, rgb_
     return out
 
 
+def synthetic_discriminator_state_dict(shapes: dict, seed: int = 0) -> dict:
+    """Same idea for a ``Discriminator.state_dict()``: unit-normal weights, 0.1 * N(0, 1) biases, FIR kernels left out."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    out = {}
+    for key in sorted(shapes):
+        if key.endswith(".kernel"):
+            continue
+        r = torch.randn(tuple(shapes[key]), generator=g, dtype=torch.float32)
+        out[key] = 0.1 * r if key.endswith(".bias") else r
+    return out
+
+
 def load_synthetic(generator, seed: int = 0, rgb_gain: float = 1.0):
     """Overwrites ``generator``'s parameters and noise buffers in place with the synthetic recipe."""
     sd = generator.state_dict()

@@ -12,7 +12,8 @@ Per step and rank (with the dead branch removed):
                                                            walk by l2i_walk_linear_bwd / the MLP kernels
     all-reduce(mean) of the flat walk gradient             the ONLY collective (NCCL over NVLink)
     Adam(lr, betas=(0.5, 0.99)).step()                     transform_base.py:329-331
-The discriminator / VGG terms are outside the accelerated path (``--no_gan_loss --no_content_loss``).
+The discriminator / VGG terms (TransformGraph.optimizeParametersAll without ``--no_gan_loss --no_content_loss``) are not part of
+this fused step: the discriminator runs on the repository's blur / bias-act kernels + cuDNN, VGG19 is stock PyTorch.
 """
 from __future__ import annotations
 
