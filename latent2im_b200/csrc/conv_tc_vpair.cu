@@ -294,8 +294,6 @@ conv_tc_vpair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           up[1][c] += fmaf(e.fir[1], h[1], e.fir[3] * h[2]);
         }
       }
-      if (p.has_skip || p.has_noise) mbar_arrive(&patch_empty[buf]);   // patch values are in registers
-
       if (e.wr != nullptr && ok) {
         float* dst = e.fused_skip ? e.skip_out : e.rgb_part;
 #pragma unroll
@@ -305,6 +303,9 @@ conv_tc_vpair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           pl[p.W] = rgb[1][c] + up[1][c];
         }
       }
+      // Hand the patch buffer back only after the stores that consume the loaded values have been issued: an
+      // mbarrier.arrive does not wait for shared-memory loads that are still queued.
+      if (p.has_skip || p.has_noise) mbar_arrive(&patch_empty[buf]);
     }
   }
 
