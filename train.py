@@ -24,7 +24,7 @@ import torch
 import torch.distributed as dist
 
 
-def main(argv=None):
+def main(argv=None, multi_attr=False):
     from latent2im_b200 import graphs, parallel
     from latent2im_b200.options import TrainOptions
     from latent2im_b200.utils import image, util
@@ -35,6 +35,8 @@ def main(argv=None):
     t.parser.add_argument("--amp", action="store_true", help="run the stock ResNet-50 regressor under bf16 autocast + channels_last")
     rank, world, local = parallel.world_info()
     opt = t.parse(argv, print_opt=(rank == 0))
+    if multi_attr and not any(a.startswith("--epochs") for a in (sys.argv[1:] if argv is None else argv)):
+        opt.epochs = 3                                        # train_multi_attr.py:54 hard-codes three epochs
     assert torch.cuda.is_available(), "train.py needs a CUDA device (there is no CPU fallback)"
     if opt.gpu and world == 1:
         os.environ["CUDA_VISIBLE_DEVICES"] = opt.gpu
@@ -57,17 +59,37 @@ def main(argv=None):
 
     kw = util.set_graph_kwargs(opt)
     g = graphs.find_model_using_name(opt.model, opt.transform)(**kw)
-    attr_list = kw["attrList"]
+    out_dir = train_loop(g, opt, constants, graph_util, kw["attrList"], rank, world, multi_attr=multi_attr)
+    if world > 1:
+        dist.destroy_process_group()
+    return out_dir
+
+
+def multi_attr_targets(alpha_org, alpha_delta):
+    """Intended semantics of ``train_multi_attr.py`` (reference train_multi_attr.py:113 unpacks two values; the
+    two-value ``get_alphas`` is graphs/pggan/transform_base.py:358-364): the sampled value is a DELTA on the current
+    regressor prediction, the regression target is the prediction moved by it and clamped to [0, 1], and the walk is
+    driven by the clamped difference."""
+    alpha_target = torch.clamp(alpha_org + alpha_delta, min=0, max=1)
+    return alpha_target, alpha_target - alpha_org
+
+
+def train_loop(g, opt, constants, graph_util, attr_list, rank=0, world=1, multi_attr=False):
+    """The iteration loop of reference train.py:25-132 / train_multi_attr.py:46-170 over any object with the
+    TransformGraph method set (``g.device`` decides where the batches go)."""
+    from latent2im_b200.utils import image
     out_dir = opt.output_dir
+    log = logging.getLogger("latent2im.train")
     if rank == 0:
         os.makedirs(out_dir, exist_ok=True)
-        log = logging.getLogger("latent2im.train")
         log.setLevel(logging.INFO)
         for h in list(log.handlers):
             log.removeHandler(h)
         log.addHandler(logging.FileHandler(os.path.join(out_dir, "log.txt"), mode="w"))
     b = constants.BATCH_SIZE
     global_b = b * world
+    losses = []
+    tag = "alpha night" if multi_attr else "alpha"          # the two reference scripts label the column differently
     for epoch in range(opt.epochs):
         inputs = graph_util.graph_input(g, opt.num_samples, seed=epoch)      # identical on every rank (seeded numpy)
         np.random.seed(100003 * epoch + 17)                                   # same target stream on every rank (SURVEY 8e)
@@ -78,21 +100,26 @@ def main(argv=None):
             t0 = time.time()
             rows = slice(i * global_b + rank * b, i * global_b + (rank + 1) * b)
             zs = inputs["z"][rows]
-            z = torch.Tensor(zs).cuda()
+            z = torch.Tensor(zs).to(g.device)
             with torch.no_grad():
                 w = g.get_w(z)
                 out_zs = g.get_logits({"w": w})
                 alpha_org = g.get_reg_preds(out_zs)
             ag, at, _ = g.get_train_alpha(zs, N_attr=len(attr_list), trainEmbed=opt.trainEmbed)
-            ag_t = torch.tensor(ag).float().cuda()
-            eps = g.get_alphas(alpha_org, ag_t)
+            ag_t = torch.tensor(ag).float().to(g.device)
+            if multi_attr:
+                target, eps = multi_attr_targets(alpha_org, ag_t)
+            else:
+                target, eps = ag_t, g.get_alphas(alpha_org, ag_t)
             w_new = g.get_w_new_tensor(w, eps, layers=opt.layers)
             out = g.get_logits({"w": w_new})
-            loss = g.optimizeParametersAll({"w": w_new, "org": out_zs, "logit": out, "alpha": ag_t}, trainEmbed=opt.trainEmbed,
+            loss = g.optimizeParametersAll({"w": w_new, "org": out_zs, "logit": out, "alpha": target}, trainEmbed=opt.trainEmbed,
                                            updateGAN=opt.updateGAN, no_content_loss=opt.no_content_loss, no_gan_loss=opt.no_gan_loss)
+            if multi_attr:
+                losses.append(loss.detach())     # kept on the device: loss_values.npy is written once, at the end
             if rank == 0 and i % opt.log_every == 0:
-                log.info("T, epc, bst, lss, alpha: {}, {}, {}, {}, {}".format(time.time() - t0, epoch, i * global_b,
-                                                                                  loss.item(), round(float(at[0]), 2)))
+                log.info("T, epc, bst, lss, {}: {}, {}, {}, {}, {}".format(tag, time.time() - t0, epoch, i * global_b,
+                                                                          loss.item(), round(float(at[0]), 2)))
             if rank == 0 and i % opt.model_save_freq == 0:
                 u8 = g.clip_ims(out.detach().float().cpu().numpy()).transpose(0, 2, 3, 1)
                 image.save_im(image.imgrid(u8, cols=len(u8)), os.path.join(out_dir, "results", "{}_{}_logit_{:.2f}".format(epoch, i * global_b, float(at[0]))))
@@ -100,10 +127,11 @@ def main(argv=None):
             g.save_multi_models("{}/model_w_{}".format(out_dir, epoch), None)
     if rank == 0:
         g.save_multi_models("{}/model_w_{}_final".format(out_dir, opt.epochs), None)
+        if multi_attr:   # train_multi_attr.py:224-226 (the matplotlib plot of the same values is left to the user)
+            np.save(os.path.join(out_dir, "loss_values.npy"),
+                    torch.stack(losses).double().cpu().numpy() if losses else np.zeros(0))
         for h in list(log.handlers):
             h.close()
-    if world > 1:
-        dist.destroy_process_group()
     return out_dir
 
 
