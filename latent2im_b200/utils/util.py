@@ -1,4 +1,5 @@
 """Reference utils/util.py:5-121 for the two transforms on the path (face, scene)."""
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -23,7 +24,10 @@ def set_graph_kwargs(opt):
     kw = dict(lr=opt.learning_rate, walk_type=opt.walk_type, loss=opt.loss, trainEmbed=opt.trainEmbed)
     if opt.transform not in ("face", "scene"):
         raise NotImplementedError("transform %r is outside the accelerated path (face | scene)" % opt.transform)
-    names, table = _read_attr_table(opt.attrPath)
+    # the reference's default is '' (options/train_options.py:38) and the lists live in its dataset/ directory
+    attr_path = opt.attrPath or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dataset",
+                                             "attributes_celeba.txt" if opt.transform == "face" else "attributes_scene.txt")
+    names, table = _read_attr_table(attr_path)
     kw["attrList"] = opt.attrList.split(",") if opt.attrList else names
     kw["attrTable"] = table
     try:
