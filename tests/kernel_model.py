@@ -73,6 +73,49 @@ def _composite_upconv(x, wc, H):
     return out
 
 
+def rowfold_weights(wt, f):
+    """Mirrors pack_uprow_weight_kernel (conv_tc_uprow.cu): only the HORIZONTAL blur is folded into the weights.
+    H[u][2n+b] = sum_j f[j] t[u][2n+b-1+j],  t[u][v] = sum_kw W[kh][kw] x[.][(v-kw)/2]  =>  per (kh, dx = -1..1, b):
+    Wr[kh][dx][b] = sum_{j : kw = b + j - 1 - 2 dx in [0,2]} f[j] W[kh][kw].   Returns [3 kh][3 dx][2 b][Cout][Cin]."""
+    cout, cin = wt.shape[:2]
+    wr = wt.new_zeros(3, 3, 2, cout, cin)
+    for kh in range(3):
+        for dx in (-1, 0, 1):
+            for b in range(2):
+                for j in range(4):
+                    kw = b + j - 1 - 2 * dx
+                    if 0 <= kw <= 2:
+                        wr[kh, dx + 1, b] += f[j] * wt[:, :, kh, kw]
+    return wr
+
+
+def _rowfold_upconv(x, wr, f, H):
+    """Row-marching fused up-conv (conv_tc_uprow.cu): horizontally blurred transposed-conv rows H[u], u = -1 .. 2H+1
+    (u = 2m + py gathers kh = py (mod 2) from input row m - kh/2, zero outside), then the vertical 4-tap FIR
+    out[oy] = sum_i f[i] H[oy - 1 + i].   x: [B,H,H,Cin] -> [B,2H,2H,Cout]."""
+    b_, _, W, cin = x.shape
+    cout = wr.shape[3]
+    xp = x.new_zeros(b_, H + 2, W + 2, cin)          # zero border = TMA out-of-bounds fill
+    xp[:, 1:H + 1, 1:W + 1] = x
+    rows = {}
+    for u in range(-1, 2 * H + 2):
+        acc = x.new_zeros(b_, W, 2, cout)
+        for kh in range(3):
+            if (u - kh) % 2:
+                continue
+            m = (u - kh) // 2                         # input row; -1 and H read the zero border
+            if m < -1 or m > H:
+                continue
+            for dx in (-1, 0, 1):
+                acc = acc + torch.einsum("bwc,poc->bwpo", xp[:, m + 1, 1 + dx:1 + dx + W], wr[kh, dx + 1])
+        rows[u] = acc.reshape(b_, 2 * W, cout)
+    out = x.new_zeros(b_, 2 * H, 2 * W, cout)
+    for oy in range(2 * H):
+        for i in range(4):
+            out[:, oy] += f[i] * rows[oy - 1 + i]
+    return out
+
+
 def _upsample2x(skip, f):
     """skip: [B,3,h,w] -> [B,3,2h,2w]; mirrors upsample2x_at (conv_common.cuh)."""
     b, c, h, w = skip.shape
@@ -128,7 +171,10 @@ def fused_forward_model(sd, latent, noise, spec, dtype=torch.float64, composite=
         nw, bias = sd[name + ".noise.weight"], sd[name + ".activate.bias"]
         H = x.shape[1]
         if up and composite:
-            v = _composite_upconv(x, composite_weights(wt, f), H) * d[:, None, None, :]
+            if composite == "row":
+                v = _rowfold_upconv(x, rowfold_weights(wt, f), f, H) * d[:, None, None, :]
+            else:
+                v = _composite_upconv(x, composite_weights(wt, f), H) * d[:, None, None, :]
             v = v + nw * nz.permute(0, 2, 3, 1) + bias
             y = torch.where(v > 0, v, 0.2 * v) * math.sqrt(2)
             acts[name] = y.permute(0, 3, 1, 2)

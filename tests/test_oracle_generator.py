@@ -42,6 +42,17 @@ def test_composite_upconv_model_equals_oracle():
         assert (a - inter[name]).abs().max() < 1e-11, name
 
 
+def test_rowfold_upconv_model_equals_oracle():
+    """conv_transpose2d(stride 2) + blur == horizontally folded transposed-conv rows (pack_uprow_weight_kernel) followed
+    by the vertical 4-tap FIR over rows u = -1 .. 2H+1 (conv_tc_uprow.cu), including the image borders."""
+    spec, sd, lat, noise = _setup()
+    ref, inter = generator_forward_ref(sd, lat, noise, spec, return_intermediates=True)
+    img, acts, _ = fused_forward_model(sd, lat, noise, spec, composite="row")
+    assert (img - ref).abs().max() < 1e-11
+    for name, a in acts.items():
+        assert (a - inter[name]).abs().max() < 1e-11, name
+
+
 def test_modulation_is_input_scaling_identity():
     """weight modulation + grouped conv == scale input channels, shared conv, scale outputs by demod."""
     spec, sd, lat, _ = _setup()
