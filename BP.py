@@ -27,6 +27,7 @@ def build_parser():
     p.add_argument("--latent_dim", type=int, default=512)
     p.add_argument("--batch_size", type=int, default=1)
     p.add_argument("--ckpt_path", type=str, default=os.environ.get("L2I_G_PATH", ""))
+    p.add_argument("--allow_random_init", action="store_true")
     p.add_argument("--gpu", type=str, default="0")
     p.add_argument("--n_loops", type=int, default=500)
     p.add_argument("--resolution", type=int, default=256, choices=[32, 64, 128, 256, 512, 1024])
@@ -68,7 +69,14 @@ def run(args, generator=None, device=None):
         device = torch.device("cuda", torch.cuda.current_device())
         generator = Generator(args.resolution, args.latent_dim, 8)
         if args.ckpt_path and os.path.exists(args.ckpt_path):
-            generator.load_state_dict(torch.load(args.ckpt_path, map_location="cpu", weights_only=False)["g_ema"], strict=False)
+            res = generator.load_state_dict(torch.load(args.ckpt_path, map_location="cpu", weights_only=False)["g_ema"], strict=False)
+            bad = [k for k in res.missing_keys if not (k.endswith(".kernel") or k.startswith("noises."))] + list(res.unexpected_keys)
+            if bad:
+                print(f"BP.py: WARNING: {args.ckpt_path}: missing / unexpected keys {bad[:8]}", file=sys.stderr)
+        elif os.environ.get("L2I_ALLOW_RANDOM_INIT", "0") in ("0", "") and not getattr(args, "allow_random_init", False):
+            raise FileNotFoundError(f"generator checkpoint not found: {args.ckpt_path!r} (--allow_random_init to invert on random weights)")
+        else:
+            print("BP.py: WARNING: no generator checkpoint: inverting against RANDOM-INIT weights", file=sys.stderr)
         generator.set_native(dtype={"fp32": torch.float32, "bf16": torch.bfloat16}[args.dtype], max_batch=args.batch_size)
         generator = generator.to(device).eval()
     perceptual = GramPerceptualLoss(args.vgg_path).to(device) if args.vgg_path else None

@@ -21,6 +21,7 @@ import argparse
 import ctypes as C
 import json
 import os
+os.environ.setdefault("L2I_ALLOW_RANDOM_INIT", "1")   # synthetic-weight benchmark
 import subprocess
 import sys
 import threading

@@ -30,6 +30,7 @@ void refresh_kernel_switches() {
   s.ares = flag("L2I_ARES", 1) != 0;
   s.vpair = flag("L2I_VPAIR", 1) != 0;
   s.fir_simt = flag("L2I_FIR_SIMT", 0) != 0;
+  s.uprow = flag("L2I_UPROW", 1) != 0;
   g_switches = s;
 }
 

@@ -1,0 +1,441 @@
+// Row-marching fused up-conv: stride-2 transposed 3x3 conv + 4x4 blur + noise + bias + leaky-relu + next-style scale in
+// ONE tcgen05 kernel with 2x the reference's MACs (the composite 6x6 formulation in conv_tc*.cu issues 4x) and no
+// shared-memory traffic for the FIR.   Reference: ModulatedConv2d.forward upsample branch + Blur (networks.py:245-256,
+// 72-88), NoiseInjection (:275-286), FusedLeakyReLU (op/fused_act.py:51-86).
+//
+// Formulation (checked in float64 by tests/kernel_model.py::_rowfold_upconv):
+//   t[u][v]      = sum_{kh,kw} W[kh][kw] x[(u-kh)/2][(v-kw)/2]           (conv_transpose2d, stride 2, rows u = -1 .. 2H+1)
+//   Hb[u][2n+b]  = sum_j f[j] t[u][2n+b-1+j] = sum_{kh == u (mod 2)} sum_{dx=-1..1} Wr[kh][dx][b] x[(u-kh)/2][n+dx]
+//   out[oy][ox]  = sum_i f[i] Hb[oy-1+i][ox]
+// Only the HORIZONTAL blur is folded into the weights (Wr, pack_uprow_weight_kernel).  One GEMM row (TMEM lane) is one input
+// column n of a 128-column segment, the GEMM N = (b, co) enumerates the two output pixels 2n+b of that column, and every
+// row u of Hb is its own accumulator in a 4-slot TMEM ring.  The vertical 4-tap FIR then happens entirely inside the
+// epilogue threads: when row u lands they finish   out[u-2] = partial + f[3] Hb[u]   and rebuild
+// partial = f[0] Hb[u-2] + f[1] Hb[u-1] + f[2] Hb[u]  for out[u-1]  straight from TMEM (tcgen05.ld; each row is read three
+// times), so no lane ever needs a neighbour's value and nothing but the finished bf16 output row touches shared memory.
+//
+// A operand: input rows (128 + 2 halo columns, Cin channels as 64-channel SWIZZLE_128B planes) in a small ring; the dx
+// shifts are UMMA descriptors starting 128 B earlier / later (zero columns / rows outside the image = TMA fill).  Input row
+// m feeds rows u = 2m (kh 0), 2m+1 (kh 1), 2m+2 (kh 2), so it is loaded once and released after the kh = 2 group.
+// B operand: the 9 (kh, dx) weight tiles [N][Cin]: resident when they fit (Cin = 64), else streamed through a ring.
+// Work split: the (sample, channel part, column segment, input row) space is flattened and cut into gridDim.x equal
+// contiguous ranges; a range start costs three extra Hb rows (u0 = 2 m0 - 1 .. 2 m0 + 1 warm the FIR).
+#include <algorithm>
+
+#include "tc_epilogue.cuh"
+
+namespace l2i {
+
+using namespace tc;
+
+namespace {
+
+constexpr int kSegW = 128;                       // GEMM M: input columns per segment
+constexpr int kRowPx = kSegW + 2;                // + one halo column each side
+constexpr int kPlaneBytes = kRowPx * 128;        // 16640: one 64-channel plane of one input row
+constexpr int kPlaneStride = (kPlaneBytes + 1023) & ~1023;   // 17408
+constexpr int kSlots = 4;                        // TMEM accumulator ring (rows of Hb)
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 128 + kEpiWarps * 32;
+
+struct UprowParams {
+  int B, H, W;                 // input grid
+  int Cout;                    // all output channels of the layer (pixel pitch of the output tensor)
+  int nch, nseg;               // channel parts (Cout / CO), column segments (W / 128)
+  int64_t total_rows;          // B * nch * nseg * H
+  EpiParams e;
+};
+
+__device__ __forceinline__ uint64_t uprow_desc(uint32_t addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+
+struct Run {
+  int b, ch, seg, m0, R;
+};
+
+// the r-th flattened row -> (sample, channel part, segment, input row); the run ends at the unit's last row or at r_end
+__device__ __forceinline__ Run decode_run(const UprowParams& p, int64_t r, int64_t r_end) {
+  Run q;
+  const int64_t unit = r / p.H;
+  q.m0 = (int)(r - unit * p.H);
+  q.R = (int)min((int64_t)(p.H - q.m0), r_end - r);
+  q.seg = (int)(unit % p.nseg);
+  const int64_t t = unit / p.nseg;
+  q.ch = (int)(t % p.nch);
+  q.b = (int)(t / p.nch);
+  return q;
+}
+
+// CO = output channels per work unit (GEMM N = 2 * CO), KC = Cin / 64, AS = input-row ring slots,
+// BRES = weights resident (all 9 * KC planes), else streamed: BP planes of one (kh, dx) tile per stage, WST stages.
+template <int CO, int KC, int AS, bool BRES, int BP, int WST>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                     const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ UprowParams p) {
+  constexpr int N = 2 * CO;
+  constexpr int kASlotBytes = KC * kPlaneStride;
+  constexpr int kBPlaneBytes = N * 128;
+  constexpr int kBBytes = BRES ? 9 * KC * kBPlaneBytes : WST * BP * kBPlaneBytes;
+  constexpr int kBStageBytes = BP * kBPlaneBytes;
+  constexpr int NCHK = CO / 32;                 // 32-column chunks per epilogue warp
+  constexpr uint32_t kIdesc = make_idesc_bf16(128, N, 0);
+  static_assert(KC % BP == 0, "a ring stage is BP planes of one tile");
+  static_assert(kSlots * N <= 512, "TMEM budget");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem_b = smem + AS * kASlotBytes;
+  uint8_t* smem_out = smem_b + kBBytes;          // kEpiWarps x 2 KB SWIZZLE_64B staging tiles (32 pixels x 32 channels)
+  __shared__ __align__(16) float epi_smem[3 * CO];
+  __shared__ __align__(8) uint64_t a_full[AS];
+  __shared__ __align__(8) uint64_t a_empty[AS];
+  __shared__ __align__(8) uint64_t w_full[BRES ? 1 : WST];
+  __shared__ __align__(8) uint64_t w_empty[BRES ? 1 : WST];
+  __shared__ __align__(8) uint64_t tmem_full[kSlots];
+  __shared__ __align__(8) uint64_t tmem_empty[kSlots];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_w);
+    prefetch_tmap(&tmap_o);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < AS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < (BRES ? 1 : WST); ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int s = 0; s < kSlots; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiWarps); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_smem, kSlots * N >= 512 ? 512 : 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int64_t r_begin = p.total_rows * (int64_t)blockIdx.x / gridDim.x;
+  const int64_t r_end = p.total_rows * (int64_t)(blockIdx.x + 1) / gridDim.x;
+
+  if (warp == 0) {
+    // ===================== A producer: input rows m0-1 .. m0+R of every run =====================
+    if (lane == 0) {
+      if (BRES) {
+        mbar_expect_tx(&w_full[0], 9 * KC * kBPlaneBytes);
+        for (int t = 0; t < 9; ++t)
+          for (int kc = 0; kc < KC; ++kc)
+            tma_load_3d(smem_b + (t * KC + kc) * kBPlaneBytes, &tmap_w, &w_full[0], kc * 64, 0, t);
+      }
+      uint32_t acnt = 0;
+      for (int64_t r = r_begin; r < r_end;) {
+        const Run q = decode_run(p, r, r_end);
+        for (int row = q.m0 - 1; row <= q.m0 + q.R; ++row, ++acnt) {
+          const int slot = acnt % AS;
+          mbar_wait(&a_empty[slot], ((acnt / AS) & 1) ^ 1);
+          mbar_expect_tx(&a_full[slot], KC * kPlaneBytes);
+#pragma unroll
+          for (int kc = 0; kc < KC; ++kc)
+            tma_load_4d(smem + slot * kASlotBytes + kc * kPlaneStride, &tmap_a, &a_full[slot], kc * 64, q.seg * kSegW - 1, row, q.b);
+        }
+        r += q.R;
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== B producer (streamed weights): same tile order as the MMA issuer =====================
+    if (!BRES && lane == 0) {
+      uint32_t wcnt = 0;
+      for (int64_t r = r_begin; r < r_end;) {
+        const Run q = decode_run(p, r, r_end);
+        const int nrows = 2 * q.R + 3;
+        for (int k = 0; k < nrows; ++k) {
+          const int py = (k & 1) ^ 1;                       // u = 2 m0 - 1 + k
+          for (int g = 0; g < (py ? 1 : 2); ++g) {
+            const int kh = py ? 1 : (g == 0 ? 2 : 0);
+            for (int dxi = 0; dxi < 3; ++dxi) {
+#pragma unroll
+              for (int kc = 0; kc < KC; kc += BP, ++wcnt) {
+                const int ws = wcnt % WST;
+                mbar_wait(&w_empty[ws], ((wcnt / WST) & 1) ^ 1);
+                mbar_expect_tx(&w_full[ws], kBStageBytes);
+#pragma unroll
+                for (int j = 0; j < BP; ++j)
+                  tma_load_3d(smem_b + ws * kBStageBytes + j * kBPlaneBytes, &tmap_w, &w_full[ws], (kc + j) * 64, 0,
+                              q.ch * 9 + kh * 3 + dxi);
+              }
+            }
+          }
+        }
+        r += q.R;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      if (BRES) {
+        mbar_wait(&w_full[0], 0);
+        tc_fence_after();
+      }
+      uint32_t abase = 0;      // ring index of the current run's first input row (m0 - 1)
+      uint32_t awaited = 0;    // input rows whose "full" barrier has been observed
+      uint32_t tcnt = 0, wcnt = 0;
+      for (int64_t r = r_begin; r < r_end;) {
+        const Run q = decode_run(p, r, r_end);
+        const int nrows = 2 * q.R + 3;
+        for (int k = 0; k < nrows; ++k, ++tcnt) {
+          const int py = (k & 1) ^ 1;
+          const int ml = (k + 1) >> 1;                      // ring-local index of input row m = floor(u / 2): m - (m0 - 1)
+          const int tslot = tcnt % kSlots;
+          mbar_wait(&tmem_empty[tslot], ((tcnt / kSlots) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + (uint32_t)(tslot * N);
+          uint32_t acc = 0;
+          for (int g = 0; g < (py ? 1 : 2); ++g) {
+            const int kh = py ? 1 : (g == 0 ? 2 : 0);
+            const uint32_t ai = abase + (uint32_t)(kh == 2 ? ml - 1 : ml);
+            while (awaited <= ai) {
+              mbar_wait(&a_full[awaited % AS], (awaited / AS) & 1);
+              ++awaited;
+            }
+            tc_fence_after();
+            const uint32_t a_row = smem_u32(smem + (ai % AS) * kASlotBytes);
+            for (int dxi = 0; dxi < 3; ++dxi) {
+#pragma unroll
+              for (int kc = 0; kc < KC; kc += BP) {
+                uint32_t b_stage;
+                if (BRES) {
+                  b_stage = smem_u32(smem_b + ((kh * 3 + dxi) * KC + kc) * kBPlaneBytes);
+                } else {
+                  const int ws = wcnt % WST;
+                  mbar_wait(&w_full[ws], (wcnt / WST) & 1);
+                  tc_fence_after();
+                  b_stage = smem_u32(smem_b + ws * kBStageBytes);
+                }
+#pragma unroll
+                for (int j = 0; j < BP; ++j) {
+                  const uint32_t a_tap = a_row + (uint32_t)((kc + j) * kPlaneStride + dxi * 128);
+                  const uint32_t b_tile = b_stage + (uint32_t)(j * kBPlaneBytes);
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk) {
+                    umma_bf16(tmem_d, uprow_desc(a_tap + kk * 32, 1024), uprow_desc(b_tile + kk * 32, 1024), kIdesc, acc);
+                    acc = 1;
+                  }
+                }
+                if (!BRES) {
+                  umma_commit(&w_empty[wcnt % WST]);
+                  ++wcnt;
+                }
+              }
+            }
+            // input row m-1 is dead after the kh = 2 group; the run's last input row after its kh = 1 group
+            if (kh == 2 || k == nrows - 1) umma_commit(&a_empty[ai % AS]);
+          }
+          umma_commit(&tmem_full[tslot]);
+        }
+        abase += (uint32_t)(q.R + 2);
+        r += q.R;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: vertical FIR from TMEM + noise / bias / lrelu / next-style scale =====================
+    const EpiParams& e = p.e;
+    const int ew = warp - 4;
+    const int q4 = warp & 3;                      // TMEM lane quadrant this warp may read
+    const int hb = ew >> 2;                       // output pixel parity b: columns [hb * CO, (hb + 1) * CO)
+    const int etid = threadIdx.x - 128;
+    float* s_d = epi_smem;
+    float* s_b = epi_smem + CO;
+    float* s_n = epi_smem + 2 * CO;
+    constexpr float kSqrt2 = 1.4142135623730951f;
+    const float nw = (e.noise != nullptr && e.noise_w != nullptr) ? __ldg(e.noise_w) * kSqrt2 : 0.f;
+    const float f0 = e.fir[0], f1 = e.fir[1], f2 = e.fir[2], f3 = e.fir[3];
+    uint8_t* stage_tile = smem_out + ew * 2048;
+    __nv_bfloat16* stage_out = (__nv_bfloat16*)stage_tile + lane * 32;
+    const int stage_swz = (lane >> 1) & 3;
+    const int out_W = 2 * p.W;
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(hb * CO);
+    uint32_t tcnt = 0;
+    float part[NCHK][32];
+    for (int64_t r = r_begin; r < r_end;) {
+      const Run q = decode_run(p, r, r_end);
+      const int nrows = 2 * q.R + 3;
+      // per-(sample, channel part) epilogue vectors
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int j = etid; j < CO; j += kEpiWarps * 32) {
+        const int co = q.ch * CO + j;
+        s_d[j] = (e.demod != nullptr ? __ldg(e.demod + (int64_t)q.b * e.demod_bs + co) : 1.f) * kSqrt2;
+        s_b[j] = __ldg(e.bias + co) * kSqrt2;
+        s_n[j] = e.s_next ? __ldg(e.s_next + (int64_t)q.b * e.s_next_bs + co) : 1.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int xo = 2 * (q.seg * kSegW + q4 * 32) + hb;                  // first output column of this warp's 32 pixels
+      const float* nrow = e.noise != nullptr ? e.noise + (int64_t)q.b * e.noise_bs + xo + 2 * lane : nullptr;
+
+      for (int k = 0; k < nrows; ++k, ++tcnt) {
+        const int oy = 2 * q.m0 + k - 3;                                  // output row finished by Hb row u = 2 m0 - 1 + k
+        const bool fin = k >= 3, nxt = k >= 2 && k <= 2 * q.R + 1;
+        float nz = 0.f;
+        if (fin && nrow != nullptr) nz = nw * __ldg(nrow + (int64_t)oy * out_W);
+        mbar_wait(&tmem_full[tcnt % kSlots], (tcnt / kSlots) & 1);
+        tc_fence_after();
+        if (k >= 2) {
+          const uint32_t t_u = lane_taddr + (uint32_t)((tcnt % kSlots) * N);
+          const uint32_t t_u1 = lane_taddr + (uint32_t)(((tcnt + kSlots - 1) % kSlots) * N);
+          const uint32_t t_u2 = lane_taddr + (uint32_t)(((tcnt + kSlots - 2) % kSlots) * N);
+#pragma unroll
+          for (int c = 0; c < NCHK; ++c) {
+            uint32_t v[32];
+            tmem_ld32(t_u + c * 32, v);
+            tmem_ld_wait();
+            if (fin) {
+              uint32_t o[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(fmaf(f3, __uint_as_float(v[j]), part[c][j]));
+              float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+              if (lane == 0) tma_store_wait_read();       // the previous store has finished reading the staging tile
+              __syncwarp();
+              epilogue_chunk32<EPI_ACT>(o, s_d + c * 32, s_b + c * 32, s_n + c * 32, nullptr, nullptr, nullptr, nz, false, r0, r1, r2,
+                                        stage_out, nullptr, stage_swz);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) tma_store_4d(&tmap_o, stage_tile, q.ch * CO + c * 32, xo, oy, q.b);
+            }
+            if (nxt) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) part[c][j] = f2 * __uint_as_float(v[j]);
+              tmem_ld32(t_u1 + c * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) part[c][j] = fmaf(f1, __uint_as_float(v[j]), part[c][j]);
+              tmem_ld32(t_u2 + c * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) part[c][j] = fmaf(f0, __uint_as_float(v[j]), part[c][j]);
+            }
+          }
+          // Hb[u-2] has now served out[u-3], out[u-2] and the partial of out[u-1]: hand its slot back; the run's last two too
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&tmem_empty[(tcnt + kSlots - 2) % kSlots]);
+            if (k == nrows - 1) {
+              mbar_arrive(&tmem_empty[(tcnt + kSlots - 1) % kSlots]);
+              mbar_arrive(&tmem_empty[tcnt % kSlots]);
+            }
+          }
+        }
+      }
+      r += q.R;
+    }
+    if (lane == 0) tma_store_wait_all();   // outstanding bulk stores must land before exit
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kSlots * N >= 512 ? 512 : 256);
+  }
+}
+
+template <int CO, int KC, int AS, bool BRES, int BP, int WST>
+int launch_uprow_variant(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const UprowParams& p, cudaStream_t st) {
+  constexpr int N = 2 * CO;
+  constexpr int smem = AS * KC * kPlaneStride + (BRES ? 9 * KC : WST * BP) * N * 128 + kEpiWarps * 2048 + 1024;
+  static_assert(smem + 3 * CO * 4 + 512 <= 227 * 1024, "shared memory budget");
+  auto kern = conv_tc_uprow_kernel<CO, KC, AS, BRES, BP, WST>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    L2I_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int grid = (int)std::min<int64_t>(p.total_rows, kNumSMs);
+  kern<<<grid, kThreads, smem, st>>>(ta, tw, to, p);
+  return check_launch("conv_tc_uprow");
+}
+
+// Wr[part][kh*3 + dx+1][b*CO + col][ci] = scale * sum_{j : kw = b + j - 1 - 2 dx in [0, 2]} f[j] W[part*CO + col][ci][kh][kw]
+__global__ void pack_uprow_weight_kernel(__nv_bfloat16* __restrict__ dst, const float* __restrict__ src, int Cout, int Cin,
+                                         int CO, float scale, float f0, float f1, float f2, float f3) {
+  const float f[4] = {f0, f1, f2, f3};
+  const int64_t total = (int64_t)18 * Cout * Cin;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(idx % Cin);
+    const int row = (int)((idx / Cin) % (2 * CO));
+    const int tile = (int)((idx / ((int64_t)Cin * 2 * CO)) % 9);
+    const int part = (int)(idx / ((int64_t)Cin * 2 * CO * 9));
+    const int b = row / CO, co = part * CO + row % CO;
+    const int kh = tile / 3, dx = tile % 3 - 1;
+    const float* w = src + ((int64_t)co * Cin + ci) * 9 + kh * 3;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int kw = b + j - 1 - 2 * dx;
+      if (kw >= 0 && kw <= 2) acc = fmaf(f[j], w[kw], acc);
+    }
+    dst[idx] = __float2bfloat16_rn(acc * scale);
+  }
+}
+
+int uprow_co(int Cin, int Cout) {
+  if (Cin == 64 && Cout == 32) return 32;
+  if (Cin == 128 && Cout == 64) return 64;
+  return 0;
+}
+
+}  // namespace
+
+// Layers this kernel takes (bf16 inference, no saved activations): 64 -> 32 and 128 -> 64 up-convs on >= 128-wide inputs.
+bool conv_tc_uprow_supported(const ConvGeom& g, const EpiParams& e) {
+  if (!g_switches.uprow || !tmap_available()) return false;
+  if (g.up_cout <= 0 || uprow_co(g.Cin, g.up_cout) == 0) return false;
+  if (g.W % kSegW != 0 || g.H < 2 || g.out_pair_packed || e.mode != 0 || e.wr != nullptr || e.y_out != nullptr) return false;
+  return e.out != nullptr && (uintptr_t)e.out % 16 == 0;
+}
+
+int64_t uprow_weight_elems(int Cin, int Cout) { return uprow_co(Cin, Cout) ? (int64_t)18 * Cin * Cout : 0; }
+
+int launch_pack_uprow_weight(__nv_bfloat16* dst, const float* src, int Cout, int Cin, float scale, const float* fir, cudaStream_t st) {
+  const int64_t total = (int64_t)18 * Cout * Cin;
+  const int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)kNumSMs * 8);
+  pack_uprow_weight_kernel<<<blocks, 256, 0, st>>>(dst, src, Cout, Cin, uprow_co(Cin, Cout), scale, fir[0], fir[1], fir[2], fir[3]);
+  return check_launch("pack_uprow_weight");
+}
+
+// in: [B][H][W][Cin] bf16 (already scaled by this layer's style); w: pack_uprow_weight_kernel layout; g.up_cout = Cout
+int launch_conv_tc_uprow(const void* in, const __nv_bfloat16* w, const ConvGeom& g, const EpiParams& e, cudaStream_t st) {
+  const int Cout = g.up_cout, CO = uprow_co(g.Cin, Cout);
+  UprowParams p{};
+  p.B = g.B; p.H = g.H; p.W = g.W; p.Cout = Cout; p.e = e;
+  p.nch = Cout / CO; p.nseg = g.W / kSegW;
+  p.total_rows = (int64_t)g.B * p.nch * p.nseg * g.H;
+  CUtensorMap ta, tw, to;
+  {
+    const uint64_t dims[4] = {(uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
+    const uint64_t str[4] = {2, (uint64_t)g.Cin * 2, (uint64_t)g.W * g.Cin * 2, (uint64_t)g.H * g.W * g.Cin * 2};
+    const uint32_t box[4] = {64, kRowPx, 1, 1};
+    L2I_TRY(make_tmap(&ta, in, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)g.Cin, (uint64_t)(2 * CO), (uint64_t)(9 * p.nch)};
+    const uint64_t str[3] = {2, (uint64_t)g.Cin * 2, (uint64_t)2 * CO * g.Cin * 2};
+    const uint32_t box[3] = {64, (uint32_t)(2 * CO), 1};
+    L2I_TRY(make_tmap(&tw, w, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  {
+    // output NHWC [B][2H][2W][Cout] bf16; an epilogue warp stores 32 channels of every other pixel of 64 consecutive pixels
+    const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)(2 * g.W), (uint64_t)(2 * g.H), (uint64_t)g.B};
+    const uint64_t str[4] = {2, (uint64_t)Cout * 2, (uint64_t)2 * g.W * Cout * 2, (uint64_t)4 * g.H * g.W * Cout * 2};
+    const uint32_t box[4] = {32, 64, 1, 1};
+    const uint32_t estr[4] = {1, 2, 1, 1};
+    L2I_TRY(make_tmap_strided(&to, e.out, 4, dims, str, box, estr, CU_TENSOR_MAP_SWIZZLE_64B));
+  }
+  if (CO == 32) return launch_uprow_variant<32, 1, 4, true, 1, 1>(ta, tw, to, p, st);
+  return launch_uprow_variant<64, 2, 2, false, 2, 4>(ta, tw, to, p, st);
+}
+
+}  // namespace l2i

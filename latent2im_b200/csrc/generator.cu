@@ -257,6 +257,7 @@ extern "C" int l2i_generator_create(l2i_generator_t** out, int size, int style_d
     L.composite = dtype == L2I_BF16 && L.up && g->conv_impl != 1 && L.res_out >= g->composite_min_res && L.cout % 32 == 0 &&
                   L.cin % 64 == 0;
     if (rc == L2I_OK && L.composite) rc = dev_alloc(g, &L.w_comp, (int64_t)36 * L.cin * L.cout);
+    if (rc == L2I_OK && L.composite && uprow_weight_elems(L.cin, L.cout) > 0) rc = dev_alloc(g, &L.w_uprow, uprow_weight_elems(L.cin, L.cout));
     if (rc != L2I_OK) return fail(rc);
   }
 
@@ -350,6 +351,7 @@ extern "C" int l2i_generator_finalize(l2i_generator_t* g, void* stream) {
     if (L.w_vpair) L2I_TRY(launch_pack_vpair_weight(L.w_vpair, P(g, L.name + ".conv.weight"), scale, st));
     if (L.w_quad) L2I_TRY(launch_pack_quad_weight(L.w_quad, P(g, L.name + ".conv.weight"), scale, st));
     if (L.w_comp) L2I_TRY(launch_pack_composite_weight(L.w_comp, P(g, L.name + ".conv.weight"), L.cout, L.cin, scale, g->fir, st));
+    if (L.w_uprow) L2I_TRY(launch_pack_uprow_weight(L.w_uprow, P(g, L.name + ".conv.weight"), L.cout, L.cin, scale, g->fir, st));
     L2I_TRY(launch_scale_copy(g->mod_w_all + (int64_t)L.s_off * D, P(g, L.name + ".conv.modulation.weight"),
                               (int64_t)L.cin * D, mod_scale, st));
     L2I_TRY(launch_scale_copy(g->mod_b_all + L.s_off, P(g, L.name + ".conv.modulation.bias"), L.cin, 1.f, st));
@@ -463,7 +465,8 @@ extern "C" int l2i_generator_forward(l2i_generator_t* g, const float* latent, in
       const double px_in = (double)B * L.res_in * L.res_in, px_out = (double)B * L.res_out * L.res_out;
       auto* sg_c = g->seg_begin(L.name + "/upconv+blur_act", 0, 2.0 * 9 * L.cin * L.cout * px_in,
                                 (px_in * L.cin + px_out * L.cout) * es + px_out * 4.0, st);
-      if (conv_tc_halo_supported(geom, e)) L2I_TRY(launch_conv_tc_halo(g->act[cur], L.w_comp, geom, e, st));
+      if (L.w_uprow != nullptr && conv_tc_uprow_supported(geom, e)) L2I_TRY(launch_conv_tc_uprow(g->act[cur], L.w_uprow, geom, e, st));
+      else if (conv_tc_halo_supported(geom, e)) L2I_TRY(launch_conv_tc_halo(g->act[cur], L.w_comp, geom, e, st));
       else if (conv_tc_ares_supported(geom, e)) L2I_TRY(launch_conv_tc_ares(g->act[cur], L.w_comp, geom, e, st));
       else if (conv_tc_supported(geom, e)) L2I_TRY(launch_conv_tc(g->act[cur], L.w_comp, geom, e, st));
       else { set_error("generator: composite up-conv of %s is not supported by the tcgen05 kernels", L.name.c_str()); return L2I_ERR_UNSUPPORTED; }

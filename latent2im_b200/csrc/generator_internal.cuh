@@ -24,6 +24,10 @@ int launch_pack_vpair_weight(__nv_bfloat16* dst, const float* src, float scale, 
 bool conv_tc_quad_supported(const ConvGeom& g, const EpiParams& e);
 int launch_conv_tc_quad(const void* in, const __nv_bfloat16* w, const ConvGeom& g, const EpiParams& e, cudaStream_t st);
 int launch_pack_quad_weight(__nv_bfloat16* dst, const float* src, float scale, cudaStream_t st);
+bool conv_tc_uprow_supported(const ConvGeom& g, const EpiParams& e);
+int launch_conv_tc_uprow(const void* in, const __nv_bfloat16* w, const ConvGeom& g, const EpiParams& e, cudaStream_t st);
+int64_t uprow_weight_elems(int Cin, int Cout);
+int launch_pack_uprow_weight(__nv_bfloat16* dst, const float* src, int Cout, int Cin, float scale, const float* fir, cudaStream_t st);
 int launch_pack_composite_weight(__nv_bfloat16* dst, const float* src, int Cout, int Cin, float scale, const float* fir, cudaStream_t st);
 template <typename T, typename TIN>
 int launch_blur_act(void*, void*, const void*, int, int, int, int, int, int, const float*, int64_t, const float*,
@@ -64,6 +68,7 @@ struct StyledConvLayer {
   __nv_bfloat16* w_vpair = nullptr;  // 64 -> 64 plain layers: [kw][2-kh][64][64] tiles for the vertical-pair kernel (conv_tc_vpair.cu)
   __nv_bfloat16* w_quad = nullptr;   // 32 -> 32 plain layers: [8][128][64] 2x2-block weight matrix (conv_tc_quad.cu)
   __nv_bfloat16* w_comp = nullptr;   // composite up-conv (transposed conv + blur folded): [9][4*Cout][Cin], rows (phase, co)
+  __nv_bfloat16* w_uprow = nullptr;  // row-marching fused up-conv (conv_tc_uprow.cu): [Cout/CO][9 = (kh, dx)][2*CO = (b, co)][Cin], horizontal blur folded
   bool composite = false;            // inference forward of this up layer runs the composite kernel (no t intermediate)
   bool split = false;                // tensor-core path uses hi + lo weights (K doubled) to remove the weight rounding error
   float* w_f32_t = nullptr;          // [9][Cout][Cin] fp32, data-gradient convs (training only)

@@ -18,8 +18,9 @@ reg_path = os.environ.get("L2I_REG_PATH", "/path/003_dict.model")
 g_path = os.environ.get("L2I_G_PATH", "/path/550000.pt")
 # torchvision vgg19 state_dict for the content loss (the reference downloads it: models.vgg19(pretrained=True))
 vgg_path = os.environ.get("L2I_VGG_PATH", "")
-# with no checkpoint on disk the modules keep their random initialisation (benchmarks, tests)
-allow_random_init = True
+# A missing checkpoint is an error, as in the reference (torch.load raises).  Benchmarks and tests, which run on random-init
+# weights of the real architecture, opt in explicitly: L2I_ALLOW_RANDOM_INIT=1 or --allow_random_init.
+allow_random_init = os.environ.get("L2I_ALLOW_RANDOM_INIT", "0") not in ("0", "")
 compute_dtype = "fp32" if os.environ.get("L2I_DTYPE", "bf16").lower() in ("fp32", "f32", "float32") else "bf16"
 walk_is_mlp = False
 # stock ResNet-50 regressor under bf16 autocast + channels_last (train.py --amp); False = the reference's fp32 arithmetic

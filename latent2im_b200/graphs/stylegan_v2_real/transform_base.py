@@ -55,6 +55,24 @@ def _layer_mask(n, layers):
     return m
 
 
+
+def _missing_checkpoint(what, path):
+    """The reference fails hard in torch.load; random weights are only for benchmarks / tests that ask for them."""
+    if not getattr(constants, "allow_random_init", False):
+        raise FileNotFoundError(f"{what} checkpoint not found: {path!r} (set L2I_ALLOW_RANDOM_INIT=1 / --allow_random_init "
+                                f"to run on random-init weights)")
+    import warnings
+    warnings.warn(f"{what} checkpoint {path!r} not found: running on RANDOM-INIT weights (allow_random_init)", stacklevel=2)
+
+
+def _report_load(result, path):
+    """load_state_dict(strict=False) result: FIR-kernel / noise buffers may legitimately differ, anything else is loud."""
+    missing = [k for k in result.missing_keys if not (k.endswith(".kernel") or k.startswith("noises."))]
+    if missing or result.unexpected_keys:
+        import warnings
+        warnings.warn(f"{path}: missing keys {missing[:8]}{'...' if len(missing) > 8 else ''}, unexpected keys "
+                      f"{list(result.unexpected_keys)[:8]}", stacklevel=2)
+
 class _WalkLinearFn(Function):
     @staticmethod
     def forward(ctx, w_param, alpha, mask, n_latent, *ws):
@@ -305,9 +323,9 @@ class TransformGraph:
         gen = Generator(constants.resolution, constants.DIM_Z, 8)
         if os.path.exists(constants.g_path):
             ckpt = torch.load(constants.g_path, map_location="cpu", weights_only=False)
-            gen.load_state_dict(ckpt["g_ema"], strict=False)
-        elif not getattr(constants, "allow_random_init", True):
-            raise FileNotFoundError(constants.g_path)
+            _report_load(gen.load_state_dict(ckpt["g_ema"], strict=False), constants.g_path)
+        else:
+            _missing_checkpoint("generator", constants.g_path)
         dtype = {"fp32": torch.float32, "bf16": torch.bfloat16}[getattr(constants, "compute_dtype", "bf16")]
         gen.set_native(dtype=dtype, max_batch=constants.BATCH_SIZE)
         module = _Module()
@@ -321,8 +339,8 @@ class TransformGraph:
         if os.path.exists(constants.reg_path):
             ckpt = torch.load(constants.reg_path, map_location="cpu", weights_only=False)
             model.load_state_dict(ckpt["model"])
-        elif not getattr(constants, "allow_random_init", True):
-            raise FileNotFoundError(constants.reg_path)
+        else:
+            _missing_checkpoint("attribute regressor", constants.reg_path)
         model = model.to(self.device).eval()
         if getattr(constants, "reg_amp", False):
             model = model.to(memory_format=torch.channels_last)
@@ -388,7 +406,7 @@ class TransformGraph:
             if os.path.exists(constants.g_path):
                 ckpt = torch.load(constants.g_path, map_location="cpu", weights_only=False)
                 if "d" in ckpt:
-                    d.load_state_dict(ckpt["d"], strict=False)
+                    _report_load(d.load_state_dict(ckpt["d"], strict=False), constants.g_path)
             d = d.to(self.device).eval()
             for p in d.parameters():
                 p.requires_grad_(False)   # frozen: only the data gradient flows back to the walk
@@ -405,8 +423,8 @@ class TransformGraph:
             path = getattr(constants, "vgg_path", "")
             if path and os.path.exists(path):
                 full.load_state_dict(torch.load(path, map_location="cpu", weights_only=False))
-            elif not getattr(constants, "allow_random_init", True):
-                raise FileNotFoundError(path)
+            else:
+                _missing_checkpoint("VGG19", path)
             # out-of-place ReLUs: the conv outputs are loss operands (the reference swaps them too, transform_base.py:439-441)
             vgg = torch.nn.Sequential(*[torch.nn.ReLU(inplace=False) if isinstance(m, torch.nn.ReLU) else m
                                         for m in full.features[:8]]).to(self.device).eval()

@@ -24,8 +24,11 @@ class EditPipeline:
         if self.device.type != "cuda":
             raise RuntimeError("EditPipeline needs a CUDA device (there is no CPU fallback)")
         dim, size = generator.style_dim, generator.size
-        self.z_host = torch.empty(batch, dim, dtype=torch.float32).pin_memory()
-        self.alpha_host = torch.empty(batch, n_attr, dtype=torch.float32).pin_memory()
+        # inputs are double-buffered like the outputs: with sync=False the host may fill buffer k^1 while the
+        # host->device copy out of buffer k is still queued behind the previous call's kernels
+        self.z_hosts = [torch.empty(batch, dim, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.alpha_hosts = [torch.empty(batch, n_attr, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.h2d_done = [None, None]       # event: host->device copies out of pinned input buffer k have finished
         self.out_hosts = [torch.empty(batch, size, size, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
         self.out_devs = [torch.empty(batch, size, size, 3, dtype=torch.uint8, device=self.device) for _ in range(2)]
         self.copy_stream = torch.cuda.Stream(self.device)
@@ -35,13 +38,13 @@ class EditPipeline:
         self._noise_pool, self._noise_pool_batch, self._noise_free, self._noise_j = None, None, None, 0
         self.copy_done = [None, None]      # event: device->host copy out of buffer k has finished
         self._k = 0
-        self.z_dev = torch.empty(batch, dim, dtype=torch.float32, device=self.device)
-        self.alpha_dev = torch.empty(batch, n_attr, dtype=torch.float32, device=self.device)
+        self.z_devs = [torch.empty(batch, dim, dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.alpha_devs = [torch.empty(batch, n_attr, dtype=torch.float32, device=self.device) for _ in range(2)]
         generator.set_native(max_batch=batch)
 
     @property
     def h2d_bytes(self) -> int:
-        return self.z_host.numel() * 4 + self.alpha_host.numel() * 4
+        return self.z_hosts[0].numel() * 4 + self.alpha_hosts[0].numel() * 4
 
     @property
     def d2h_bytes(self) -> int:
@@ -112,16 +115,20 @@ class EditPipeline:
     def edit(self, z, alpha, layers=None, noise=None, sync=True) -> np.ndarray:
         """``z``: [B, dim] host array / tensor (float64 from the numpy sampler is fine, it is cast to
         float32 exactly like ``torch.Tensor(z)`` in train.py:56); ``alpha``: [B, A] host."""
-        self.z_host.copy_(torch.as_tensor(z).to(torch.float32))
-        self.alpha_host.copy_(torch.as_tensor(alpha).to(torch.float32).reshape(self.batch, -1))
         main = torch.cuda.current_stream(self.device)
         k = self._k
         self._k ^= 1
+        if self.h2d_done[k] is not None:
+            self.h2d_done[k].synchronize()               # the copy engine has read pinned input buffer k (two calls ago)
+        self.z_hosts[k].copy_(torch.as_tensor(z).to(torch.float32))
+        self.alpha_hosts[k].copy_(torch.as_tensor(alpha).to(torch.float32).reshape(self.batch, -1))
         if self.copy_done[k] is not None:
-            main.wait_event(self.copy_done[k])           # buffer k is free again (copy of two calls ago)
-        self.z_dev.copy_(self.z_host, non_blocking=True)
-        self.alpha_dev.copy_(self.alpha_host, non_blocking=True)
-        self.edit_device(self.z_dev, self.alpha_dev, layers=layers, noise=noise, want_uint8=True, out_uint8=self.out_devs[k])
+            main.wait_event(self.copy_done[k])           # output buffer k is free again (copy of two calls ago)
+        self.z_devs[k].copy_(self.z_hosts[k], non_blocking=True)
+        self.alpha_devs[k].copy_(self.alpha_hosts[k], non_blocking=True)
+        self.h2d_done[k] = torch.cuda.Event()
+        self.h2d_done[k].record(main)
+        self.edit_device(self.z_devs[k], self.alpha_devs[k], layers=layers, noise=noise, want_uint8=True, out_uint8=self.out_devs[k])
         computed = torch.cuda.Event()
         computed.record(main)
         with torch.cuda.stream(self.copy_stream):

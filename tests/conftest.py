@@ -3,6 +3,8 @@ import sys
 
 import pytest
 
+os.environ.setdefault("L2I_ALLOW_RANDOM_INIT", "1")   # tests run on random-init weights of the real architecture
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

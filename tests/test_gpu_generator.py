@@ -342,3 +342,40 @@ def test_fused_uint8_epilogue_of_the_last_layer_matches_the_separate_cast():
         u8_fused = gen.synthesize(lat, noise=noise, want_uint8=True, want_float=False)
     assert torch.equal(u8_sep, u8_fused)
     assert torch.equal(u8_sep, clip_to_uint8_ref(img.cpu()).permute(0, 2, 3, 1).cuda())
+
+
+def _oracle_threads():
+    import os
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+
+
+@pytest.mark.parametrize("batch", [1, 3])
+def test_uprow_fused_upconv_matches_oracle(batch, monkeypatch):
+    """Row-marching fused up-conv (conv_tc_uprow.cu: 128 -> 64 with streamed weights, 64 -> 32 with resident weights) vs the
+    float64 oracle, layer by layer (activations of the up layers) and on the image; and vs the composite 6x6 kernels it
+    replaces (L2I_UPROW=0).  512 px with channel multiplier 1 routes the 128 -> 256 and 256 -> 512 px layers to it; batch 3
+    makes the per-CTA row ranges cross sample boundaries."""
+    from latent2im_b200.graphs.stylegan_v2_real.networks import Generator
+    _oracle_threads()
+    size = 512
+    spec = GeneratorSpec(size=size, style_dim=64, n_mlp=1, channel_multiplier=1)
+    lat = _latent(spec, batch)
+    noise = synthetic_noise(spec.num_layers, batch)
+    imgs, acts = {}, {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("L2I_UPROW", flag)
+        gen = load_synthetic(Generator(size, 64, 1, channel_multiplier=1), seed=0, rgb_gain=0.25)
+        sd = {k: v.double() for k, v in gen.state_dict().items()}
+        gen = gen.cuda()
+        gen.set_native(dtype=torch.bfloat16)
+        imgs[flag], _ = gen(lat.cuda(), input_is_latent=True, noise=[n.cuda() for n in noise])
+        if flag == "1":
+            acts = {name: gen.read_activation(name).cpu().double() for name in ("convs.11", "convs.12")}
+        assert torch.isfinite(imgs[flag]).all()
+    ref, inter = generator_forward_ref(sd, lat.double(), noise, spec, return_intermediates=True)
+    # convs.12 (up 256 -> 512, 64 -> 32) is materialised; its producer chain contains convs.10 (up 128 -> 256, 128 -> 64)
+    for name, a in acts.items():
+        rel = ((a - inter[name]) ** 2).mean().sqrt() / inter[name].std()
+        assert rel <= 2e-2, (name, rel.item())
+    assert _psnr(imgs["1"].cpu().double(), ref) >= 45.0
+    assert _psnr(imgs["1"].double(), imgs["0"].double()) >= 46.0

@@ -70,6 +70,33 @@ def test_async_double_buffering_returns_every_result():
     assert pipe.h2d_bytes == 2 * 32 * 4 + 2 * 4 and pipe.d2h_bytes == 2 * 16 * 16 * 3
 
 
+def test_async_calls_in_flight_keep_their_own_inputs():
+    """Several sync=False calls with DIFFERENT z / alpha are issued back to back before any wait: every result must be the
+    image of its own inputs (the pinned input buffers are double-buffered and guarded by an event; a single pinned
+    buffer would let call i synthesize from call i+1's latents)."""
+    spec, sd, w0, pipe = _setup(64, 64, 1, 4, torch.float32)
+    noise = [n.cuda() for n in synthetic_noise(spec.num_layers, 4)]
+    zs = [synthetic_z(4, 10 + s, 64) for s in range(6)]
+    alphas = [torch.full((4, 1), 0.1 * s) for s in range(6)]
+    expect = [pipe.edit(z, a, noise=noise, sync=True).copy() for z, a in zip(zs, alphas)]
+    # keep the GPU busy so that the host really runs ahead of the queued host->device copies
+    big = torch.randn(8192, 8192, device="cuda")
+    for _ in range(8):
+        big = big @ big.t() * 1e-4
+    got = []
+    for i, (z, a) in enumerate(zip(zs, alphas)):
+        view = pipe.edit(z, a, noise=noise, sync=False)
+        if i >= 1:                                     # result i-1 lives in the other output buffer: read it one call late
+            pipe.copy_done[(i - 1) & 1].synchronize()
+            got.append(prev.copy())
+        prev = view
+    pipe.wait()
+    got.append(prev.copy())
+    for i, (a, b) in enumerate(zip(expect, got)):
+        assert np.array_equal(a, b), i
+    assert not np.array_equal(expect[0], expect[1])
+
+
 def test_pipeline_needs_cuda():
     from latent2im_b200.graphs.stylegan_v2_real.networks import Generator
     from latent2im_b200.pipeline import EditPipeline

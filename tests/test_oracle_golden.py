@@ -94,3 +94,22 @@ def test_walks_against_reference_modules():
     assert torch.allclose(out, _t(z["nl_out"]), atol=1e-5)
     out = torch.stack(walk_nonlinear_ref(ws, alpha, emb, mlp2, layers=[1, 2]), 1)
     assert torch.allclose(out, _t(z["nl_out_layers"]), atol=1e-5)
+
+
+def test_oracle_matches_fullsize_reference_fixture_256():
+    """cfg1 size: the float64 oracle against the image the unmodified reference produced on a B200 at 256 px (batch 2)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden_ref_gpu_fullsize import CASES, fullsize_inputs
+    from latent2im_b200.graphs.stylegan_v2_real.networks import Generator
+    from latent2im_b200.synthetic import synthetic_state_dict
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_gpu_fullsize.npz"))
+    tag, size, batch, seed = CASES[0]
+    spec = GeneratorSpec(size=size)
+    shapes = {k: v.shape for k, v in Generator(size, 512, 8).state_dict().items()}
+    sd = {k: v.double() for k, v in synthetic_state_dict(shapes, seed).items()}
+    w = torch.from_numpy(z[f"{tag}_w"])
+    lat, noise, _ = fullsize_inputs(size, batch, seed, spec.n_latent, spec.num_layers, w)
+    ref = generator_forward_ref(sd, lat.double(), [n.double() for n in noise], spec)
+    err = (ref - torch.from_numpy(z[f"{tag}_image"]).double()).abs().max().item()
+    assert err <= 1e-3, err

@@ -10,6 +10,7 @@ The reference has no bf16 path (AT_DISPATCH_FLOATING_TYPES_AND_HALF) - it runs f
 import argparse
 import json
 import os
+os.environ.setdefault("L2I_ALLOW_RANDOM_INIT", "1")   # synthetic-weight benchmark
 import sys
 import time
 

@@ -3,6 +3,7 @@ batch 16/GPU) and its parts on one GPU, or data-parallel under torchrun.  Prints
 import argparse
 import json
 import os
+os.environ.setdefault("L2I_ALLOW_RANDOM_INIT", "1")   # synthetic-weight benchmark
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -32,14 +32,15 @@ def main(argv=None, multi_attr=False):
     t = TrainOptions()
     t.initialize()
     t.parser.add_argument("--log_every", type=int, default=10)
+    t.parser.add_argument("--allow_random_init", action="store_true", help="run on random-init G / R when no checkpoint is found")
     t.parser.add_argument("--amp", action="store_true", help="run the stock ResNet-50 regressor under bf16 autocast + channels_last")
     rank, world, local = parallel.world_info()
     opt = t.parse(argv, print_opt=(rank == 0))
     if multi_attr and not any(a.startswith("--epochs") for a in (sys.argv[1:] if argv is None else argv)):
         opt.epochs = 3                                        # train_multi_attr.py:54 hard-codes three epochs
-    assert torch.cuda.is_available(), "train.py needs a CUDA device (there is no CPU fallback)"
     if opt.gpu and world == 1:
-        os.environ["CUDA_VISIBLE_DEVICES"] = opt.gpu
+        os.environ["CUDA_VISIBLE_DEVICES"] = opt.gpu       # before the first CUDA call: the visible set is latched by it
+    assert torch.cuda.is_available(), "train.py needs a CUDA device (there is no CPU fallback)"
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -54,6 +55,8 @@ def main(argv=None, multi_attr=False):
     if opt.dtype:
         constants.compute_dtype = opt.dtype
     constants.walk_is_mlp = bool(opt.walk_mlp)
+    if opt.allow_random_init:
+        constants.allow_random_init = True
     if opt.amp:
         constants.reg_amp = True
 

@@ -31,12 +31,13 @@ def main(argv=None):
     v.parser.add_argument("--updateGAN", action="store_true")
     v.parser.add_argument("--size", type=int, default=None)
     v.parser.add_argument("--batch_size", type=int, default=None)
+    v.parser.add_argument("--allow_random_init", action="store_true", help="run on random-init G / R when no checkpoint is found")
     v.parser.add_argument("--cache_original", action="store_true",
                           help="compute G(w) and R(G(w)) once per batch instead of once per panel (the reference recomputes them)")
     opt, conf = v.parse(argv)
-    assert torch.cuda.is_available(), "vis_w.py needs a CUDA device (there is no CPU fallback)"
     if opt.gpu:
-        os.environ["CUDA_VISIBLE_DEVICES"] = opt.gpu
+        os.environ["CUDA_VISIBLE_DEVICES"] = opt.gpu       # before the first CUDA call: the visible set is latched by it
+    assert torch.cuda.is_available(), "vis_w.py needs a CUDA device (there is no CPU fallback)"
     out_dir = opt.output_dir or os.path.join(conf.output_dir, "images")
     os.makedirs(out_dir, exist_ok=True)
     constants = importlib.import_module("latent2im_b200.graphs." + conf.model + ".constants")
@@ -50,6 +51,8 @@ def main(argv=None):
     if getattr(conf, "dtype", None):
         constants.compute_dtype = conf.dtype
     constants.walk_is_mlp = bool(getattr(conf, "walk_mlp", False))
+    if opt.allow_random_init:
+        constants.allow_random_init = True
     g = graphs.find_model_using_name(conf.model, conf.transform)(**util.set_graph_kwargs(conf))
     g.load_multi_models(opt.save_path_w, None, trainEmbed=opt.trainEmbed, updateGAN=opt.updateGAN)
     inputs = graph_util.graph_input(g, opt.num_samples, seed=opt.noise_seed)
