@@ -109,6 +109,22 @@ int l2i_walk_combine(float* out, const float* in, int64_t in_batch_stride, int64
                      const float* coef, int B, int n_latent, int D, uint64_t layer_mask,
                      int normalize, void* stream);
 
+/* Backward of l2i_linear_fwd (wscale = bscale = gain = 1) for training the walk MLPs, i.e. what autograd runs for
+ * nn.Linear + nn.LeakyReLU in WalkMlpMultiW / WalkNonLinearW (transform_base.py:175-179, 214-217):
+ *   g = gy * (act && y <= 0 ? alpha : 1)      (y = the saved forward OUTPUT)
+ *   gx[b, k] = sum_n g[b, n] W[n, k];   gW[n, k] = sum_b g[b, n] x[b, k];   gb[n] = sum_b g[b, n]
+ * gx / gW / gb may each be NULL (not wanted).  All fp32, dense row-major. */
+int l2i_linear_bwd(float* gx, float* gW, float* gb, const float* gy, const float* y, const float* x,
+                   const float* W, int B, int N, int K, int act, float alpha, void* stream);
+
+/* Gradient of l2i_walk_combine w.r.t. d (grad w.r.t. `in` is grad_out itself):
+ *   normalize = 0: grad_d = coef * g;    normalize = 1: grad_d = (g - <g,u> u) / ||d||, u = d / ||d||
+ * grad_out: [B, n_latent, D].  d_layer_stride == 0 (one MLP output for every layer): grad_d is [B, D] = the sum over
+ * the masked layers and `scratch` ([B, n_latent, D]) is required; otherwise grad_d is [B, n_latent, D]. */
+int l2i_walk_combine_bwd(float* grad_d, float* scratch, const float* grad_out, const float* d,
+                         int64_t d_batch_stride, int64_t d_layer_stride, const float* coef, int B,
+                         int n_latent, int D, uint64_t layer_mask, int normalize, void* stream);
+
 /* -------------------------------------------------------------------------------------------- */
 /* StyleGAN2 synthesis network                                                                   */
 /* -------------------------------------------------------------------------------------------- */

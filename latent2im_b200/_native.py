@@ -34,6 +34,8 @@ _SIGNATURES = {
     "l2i_walk_linear_fwd": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _u64, _vp]),
     "l2i_walk_linear_bwd": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _u64, _vp]),
     "l2i_walk_combine": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i32, _i32, _i32, _u64, _i32, _vp]),
+    "l2i_linear_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp]),
+    "l2i_walk_combine_bwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _i32, _i32, _i32, _u64, _i32, _vp]),
     "l2i_generator_create": (_i32, [C.POINTER(_vp), _i32, _i32, _i32, _i32, C.POINTER(_f32), _i32, _f32, _i32, _i32]),
     "l2i_generator_destroy": (None, [_vp]),
     "l2i_generator_set_param": (_i32, [_vp, C.c_char_p, _vp, _i64, _vp]),

@@ -34,9 +34,23 @@ constexpr int kSegW = 128;                       // GEMM M: input columns per se
 constexpr int kRowPx = kSegW + 2;                // + one halo column each side
 constexpr int kPlaneBytes = kRowPx * 128;        // 16640: one 64-channel plane of one input row
 constexpr int kPlaneStride = (kPlaneBytes + 1023) & ~1023;   // 17408
-constexpr int kSlots = 4;                        // TMEM accumulator ring (rows of Hb)
 constexpr int kEpiWarps = 8;
+constexpr int kNoiseSlots = 4;                   // ring of 1 KB noise row segments (256 output pixels, fp32)
 constexpr int kThreads = 128 + kEpiWarps * 32;
+
+// Optional cycle accounting (compile with -DL2I_UPROW_PROF, tools/probes/uprow_prof.py): lane 0 of every warp accumulates the clocks
+// it spends in each wait and dumps them to e.rgb_part (unused by this kernel) as [block][12 warps][8] counters.
+#ifdef L2I_UPROW_PROF
+#define PROF_DECL long long prof_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long prof_t_ = clock64(); const long long prof_t0_ = prof_t_
+#define PROF_MARK(i) do { const long long n_ = clock64(); prof_[i] += n_ - prof_t_; prof_t_ = n_; } while (0)
+#define PROF_DUMP(p, warp) do { if ((threadIdx.x & 31) == 0 && (p).e.rgb_part != nullptr) { \
+    prof_[7] = clock64() - prof_t0_; long long* d_ = (long long*)(p).e.rgb_part + (((size_t)KC * 148 + blockIdx.x) * 12 + (warp)) * 8; \
+    for (int i_ = 0; i_ < 8; ++i_) d_[i_] = prof_[i_]; } } while (0)
+#else
+#define PROF_DECL
+#define PROF_MARK(i)
+#define PROF_DUMP(p, warp)
+#endif
 
 struct UprowParams {
   int B, H, W;                 // input grid
@@ -84,15 +98,23 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   constexpr int kBBytes = BRES ? 9 * KC * kBPlaneBytes : WST * BP * kBPlaneBytes;
   constexpr int kBStageBytes = BP * kBPlaneBytes;
   constexpr int NCHK = CO / 32;                 // 32-column chunks per epilogue warp
+  constexpr int kSlots = 512 / N >= 8 ? 8 : 512 / N;   // TMEM accumulator ring (rows of Hb): 8 x 64 or 4 x 128 columns
+  // Vertical FIR state per epilogue thread.  NPART = 3 (CO = 32): three running partial output rows in registers, ONE
+  // tcgen05.ld per Hb row, whose slot is handed back as soon as the load has landed.  NPART = 2 (CO = 64, register budget):
+  // two partial rows, rows u and u-1 are read, row u-1's slot is handed back after the loads.
+  constexpr int NPART = CO <= 32 ? 3 : 2;
   constexpr uint32_t kIdesc = make_idesc_bf16(128, N, 0);
   static_assert(KC % BP == 0, "a ring stage is BP planes of one tile");
-  static_assert(kSlots * N <= 512, "TMEM budget");
+  static_assert(kSlots * N <= 512 && kSlots >= 4, "TMEM budget");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_b = smem + AS * kASlotBytes;
   uint8_t* smem_out = smem_b + kBBytes;          // kEpiWarps x 2 KB SWIZZLE_64B staging tiles (32 pixels x 32 channels)
   __shared__ __align__(16) float epi_smem[3 * CO];
+  __shared__ __align__(128) float noise_smem[kNoiseSlots][2 * kSegW];
+  __shared__ __align__(8) uint64_t n_full[kNoiseSlots];
+  __shared__ __align__(8) uint64_t n_empty[kNoiseSlots];
   __shared__ __align__(8) uint64_t a_full[AS];
   __shared__ __align__(8) uint64_t a_empty[AS];
   __shared__ __align__(8) uint64_t w_full[BRES ? 1 : WST];
@@ -111,9 +133,10 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     for (int s = 0; s < AS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < (BRES ? 1 : WST); ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int s = 0; s < kSlots; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiWarps); }
+    for (int s = 0; s < kNoiseSlots; ++s) { mbar_init(&n_full[s], 1); mbar_init(&n_empty[s], kEpiWarps); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(&tmem_base_smem, kSlots * N >= 512 ? 512 : 256);
+  if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -122,6 +145,12 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   const int64_t r_begin = p.total_rows * (int64_t)blockIdx.x / gridDim.x;
   const int64_t r_end = p.total_rows * (int64_t)(blockIdx.x + 1) / gridDim.x;
 
+  // register budget: the producer / MMA warpgroup needs few, the 8 epilogue warps hold the FIR state of up to 64 channels.
+  // setmaxnreg.inc can only take what .dec released inside THIS CTA's launch allocation (384 threads x 168 registers): a
+  // request beyond it blocks forever (measured the hard way: 48 / 232 hangs).
+  static_assert(128 * 48 + kEpiWarps * 32 * 224 <= kThreads * 168, "setmaxnreg budget");
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
   if (warp == 0) {
     // ===================== A producer: input rows m0-1 .. m0+R of every run =====================
     if (lane == 0) {
@@ -157,7 +186,7 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           for (int g = 0; g < (py ? 1 : 2); ++g) {
             const int kh = py ? 1 : (g == 0 ? 2 : 0);
             for (int dxi = 0; dxi < 3; ++dxi) {
-#pragma unroll
+#pragma unroll 1
               for (int kc = 0; kc < KC; kc += BP, ++wcnt) {
                 const int ws = wcnt % WST;
                 mbar_wait(&w_empty[ws], ((wcnt / WST) & 1) ^ 1);
@@ -173,6 +202,26 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         r += q.R;
       }
     }
+  } else if (warp == 2) {
+    // ===================== noise producer: the 256-pixel fp32 noise segment of every output row, a few rows ahead ==========
+    // (a global load in the epilogue threads would be waited for by the MEMBAR of every fence.proxy.async before a TMA store)
+    if (lane == 0 && p.e.noise != nullptr) {
+      uint32_t ncnt = 0;
+      for (int64_t r = r_begin; r < r_end;) {
+        const Run q = decode_run(p, r, r_end);
+        const float* src = p.e.noise + (int64_t)q.b * p.e.noise_bs + (int64_t)(2 * q.m0) * (2 * p.W) + 2 * q.seg * kSegW;
+        for (int j = 0; j < 2 * q.R; ++j, ++ncnt) {
+          const int slot = ncnt % kNoiseSlots;
+          mbar_wait(&n_empty[slot], ((ncnt / kNoiseSlots) & 1) ^ 1);
+          mbar_expect_tx(&n_full[slot], 2 * kSegW * 4);
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           smem_u32(&noise_smem[slot][0])),
+                       "l"(src + (int64_t)j * (2 * p.W)), "r"(2 * kSegW * 4), "r"(smem_u32(&n_full[slot]))
+                       : "memory");
+        }
+        r += q.R;
+      }
+    }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
@@ -180,6 +229,7 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         mbar_wait(&w_full[0], 0);
         tc_fence_after();
       }
+      PROF_DECL;
       uint32_t abase = 0;      // ring index of the current run's first input row (m0 - 1)
       uint32_t awaited = 0;    // input rows whose "full" barrier has been observed
       uint32_t tcnt = 0, wcnt = 0;
@@ -190,7 +240,9 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           const int py = (k & 1) ^ 1;
           const int ml = (k + 1) >> 1;                      // ring-local index of input row m = floor(u / 2): m - (m0 - 1)
           const int tslot = tcnt % kSlots;
+          PROF_MARK(0);                                                   // 0: issue / loop overhead
           mbar_wait(&tmem_empty[tslot], ((tcnt / kSlots) & 1) ^ 1);
+          PROF_MARK(1);                                                   // 1: waiting for a free accumulator slot
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + (uint32_t)(tslot * N);
           uint32_t acc = 0;
@@ -198,20 +250,24 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             const int kh = py ? 1 : (g == 0 ? 2 : 0);
             const uint32_t ai = abase + (uint32_t)(kh == 2 ? ml - 1 : ml);
             while (awaited <= ai) {
+              PROF_MARK(0);
               mbar_wait(&a_full[awaited % AS], (awaited / AS) & 1);
+              PROF_MARK(2);                                               // 2: waiting for an input row
               ++awaited;
             }
             tc_fence_after();
             const uint32_t a_row = smem_u32(smem + (ai % AS) * kASlotBytes);
             for (int dxi = 0; dxi < 3; ++dxi) {
-#pragma unroll
+#pragma unroll 1
               for (int kc = 0; kc < KC; kc += BP) {
                 uint32_t b_stage;
                 if (BRES) {
                   b_stage = smem_u32(smem_b + ((kh * 3 + dxi) * KC + kc) * kBPlaneBytes);
                 } else {
                   const int ws = wcnt % WST;
+                  PROF_MARK(0);
                   mbar_wait(&w_full[ws], (wcnt / WST) & 1);
+                  PROF_MARK(3);                                           // 3: waiting for a weight stage
                   tc_fence_after();
                   b_stage = smem_u32(smem_b + ws * kBStageBytes);
                 }
@@ -239,8 +295,12 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         abase += (uint32_t)(q.R + 2);
         r += q.R;
       }
+      PROF_MARK(0);
+      PROF_DUMP(p, 1);
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     // ===================== epilogue: vertical FIR from TMEM + noise / bias / lrelu / next-style scale =====================
     const EpiParams& e = p.e;
     const int ew = warp - 4;
@@ -251,15 +311,17 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     float* s_b = epi_smem + CO;
     float* s_n = epi_smem + 2 * CO;
     constexpr float kSqrt2 = 1.4142135623730951f;
-    const float nw = (e.noise != nullptr && e.noise_w != nullptr) ? __ldg(e.noise_w) * kSqrt2 : 0.f;
+    const bool has_noise = e.noise != nullptr;
+    const float nw = (has_noise && e.noise_w != nullptr) ? __ldg(e.noise_w) * kSqrt2 : 0.f;
     const float f0 = e.fir[0], f1 = e.fir[1], f2 = e.fir[2], f3 = e.fir[3];
     uint8_t* stage_tile = smem_out + ew * 2048;
     __nv_bfloat16* stage_out = (__nv_bfloat16*)stage_tile + lane * 32;
     const int stage_swz = (lane >> 1) & 3;
-    const int out_W = 2 * p.W;
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(hb * CO);
-    uint32_t tcnt = 0;
-    float part[NCHK][32];
+    const float* my_noise = &noise_smem[0][2 * (q4 * 32 + lane) + hb];
+    PROF_DECL;
+    uint32_t tcnt = 0, ncnt = 0;
+    float pa[NCHK][32], pb[NCHK][32], pc[NPART == 3 ? NCHK : 1][32];
     for (int64_t r = r_begin; r < r_end;) {
       const Run q = decode_run(p, r, r_end);
       const int nrows = 2 * q.R + 3;
@@ -273,64 +335,100 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const int xo = 2 * (q.seg * kSegW + q4 * 32) + hb;                  // first output column of this warp's 32 pixels
-      const float* nrow = e.noise != nullptr ? e.noise + (int64_t)q.b * e.noise_bs + xo + 2 * lane : nullptr;
+#pragma unroll
+      for (int c = 0; c < NCHK; ++c)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { pa[c][j] = 0.f; pb[c][j] = 0.f; if (NPART == 3) pc[c][j] = 0.f; }
 
+      // Hb row u = 2 m0 - 1 + k.  Invariant before row k:  pa = f0 H[k-3] + f1 H[k-2] + f2 H[k-1]  (output row k-2 minus its last
+      // term),  pb = f0 H[k-2] + f1 H[k-1],  pc = f0 H[k-1]  (rows before the run's first count as absent: those output rows
+      // belong to the previous range and are not written here).
       for (int k = 0; k < nrows; ++k, ++tcnt) {
-        const int oy = 2 * q.m0 + k - 3;                                  // output row finished by Hb row u = 2 m0 - 1 + k
-        const bool fin = k >= 3, nxt = k >= 2 && k <= 2 * q.R + 1;
-        float nz = 0.f;
-        if (fin && nrow != nullptr) nz = nw * __ldg(nrow + (int64_t)oy * out_W);
+        const int oy = 2 * q.m0 + k - 3;                                  // output row finished by Hb row k
+        const bool fin = k >= 3;
+        PROF_MARK(0);                                                     // 0: arithmetic, staging stores, TMA store issue
         mbar_wait(&tmem_full[tcnt % kSlots], (tcnt / kSlots) & 1);
+        PROF_MARK(1);                                                     // 1: waiting for the Hb row (MMA)
         tc_fence_after();
-        if (k >= 2) {
-          const uint32_t t_u = lane_taddr + (uint32_t)((tcnt % kSlots) * N);
-          const uint32_t t_u1 = lane_taddr + (uint32_t)(((tcnt + kSlots - 1) % kSlots) * N);
-          const uint32_t t_u2 = lane_taddr + (uint32_t)(((tcnt + kSlots - 2) % kSlots) * N);
+        const uint32_t t_u = lane_taddr + (uint32_t)((tcnt % kSlots) * N);
+        const uint32_t t_u1 = lane_taddr + (uint32_t)(((tcnt + kSlots - 1) % kSlots) * N);
+        float nz = 0.f;
+        if (fin && has_noise) {                                           // this row's noise segment (bulk-copied by warp 2)
+          const int slot = ncnt % kNoiseSlots;
+          PROF_MARK(0);
+          mbar_wait(&n_full[slot], (ncnt / kNoiseSlots) & 1);
+          PROF_MARK(2);                                                   // 2: waiting for the noise row
+          nz = nw * my_noise[slot * 2 * kSegW];
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&n_empty[slot]);
+          ++ncnt;
+        }
 #pragma unroll
-          for (int c = 0; c < NCHK; ++c) {
-            uint32_t v[32];
-            tmem_ld32(t_u + c * 32, v);
-            tmem_ld_wait();
-            if (fin) {
-              uint32_t o[32];
+        for (int c = 0; c < NCHK; ++c) {
+          uint32_t v[32], v1[NPART == 2 ? 32 : 1];
+          tmem_ld32(t_u + c * 32, v);
+          if (NPART == 2) {
+            if (k > 0) {
+              uint32_t w1[32];
+              tmem_ld32(t_u1 + c * 32, w1);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(fmaf(f3, __uint_as_float(v[j]), part[c][j]));
-              float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-              if (lane == 0) tma_store_wait_read();       // the previous store has finished reading the staging tile
-              __syncwarp();
-              epilogue_chunk32<EPI_ACT>(o, s_d + c * 32, s_b + c * 32, s_n + c * 32, nullptr, nullptr, nullptr, nz, false, r0, r1, r2,
-                                        stage_out, nullptr, stage_swz);
-              fence_proxy_async_smem();
-              __syncwarp();
-              if (lane == 0) tma_store_4d(&tmap_o, stage_tile, q.ch * CO + c * 32, xo, oy, q.b);
-            }
-            if (nxt) {
+              for (int j = 0; j < 32; ++j) v1[j] = w1[j];
+            } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) part[c][j] = f2 * __uint_as_float(v[j]);
-              tmem_ld32(t_u1 + c * 32, v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) part[c][j] = fmaf(f1, __uint_as_float(v[j]), part[c][j]);
-              tmem_ld32(t_u2 + c * 32, v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) part[c][j] = fmaf(f0, __uint_as_float(v[j]), part[c][j]);
+              for (int j = 0; j < 32; ++j) v1[j] = 0u;
             }
           }
-          // Hb[u-2] has now served out[u-3], out[u-2] and the partial of out[u-1]: hand its slot back; the run's last two too
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            mbar_arrive(&tmem_empty[(tcnt + kSlots - 2) % kSlots]);
-            if (k == nrows - 1) {
-              mbar_arrive(&tmem_empty[(tcnt + kSlots - 1) % kSlots]);
-              mbar_arrive(&tmem_empty[tcnt % kSlots]);
+          PROF_MARK(0);
+          tmem_ld_wait();
+          PROF_MARK(3);                                                   // 3: tcgen05.ld latency
+          if (c == NCHK - 1) {
+            // NPART 3: Hb[k] is in registers, nothing will read its slot again.  NPART 2: Hb[k-1] has been read for the last time
+            // (the run's last row additionally frees its own slot).
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (NPART == 3) {
+                mbar_arrive(&tmem_empty[tcnt % kSlots]);
+              } else {
+                if (k > 0) mbar_arrive(&tmem_empty[(tcnt + kSlots - 1) % kSlots]);
+                if (k == nrows - 1) mbar_arrive(&tmem_empty[tcnt % kSlots]);
+              }
+            }
+          }
+          if (fin) {
+            uint32_t o[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(fmaf(f3, __uint_as_float(v[j]), pa[c][j]));
+            float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+            PROF_MARK(0);
+            if (lane == 0) tma_store_wait_read();         // the previous store has finished reading the staging tile
+            __syncwarp();
+            PROF_MARK(4);                                                 // 4: previous TMA store still reading the staging tile
+            epilogue_chunk32<EPI_ACT>(o, s_d + c * 32, s_b + c * 32, s_n + c * 32, nullptr, nullptr, nullptr, nz, false, r0, r1, r2,
+                                      stage_out, nullptr, stage_swz);
+            PROF_MARK(0);
+            fence_proxy_async_smem();
+            __syncwarp();
+            PROF_MARK(5);                                                 // 5: proxy fence (MEMBAR) before the TMA store
+            if (lane == 0) tma_store_4d(&tmap_o, stage_tile, q.ch * CO + c * 32, xo, oy, q.b);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = __uint_as_float(v[j]);
+            pa[c][j] = fmaf(f2, x, pb[c][j]);
+            if (NPART == 3) {
+              pb[c][j] = fmaf(f1, x, pc[c][j]);
+              pc[c][j] = f0 * x;
+            } else {
+              pb[c][j] = fmaf(f1, x, f0 * __uint_as_float(v1[j]));
             }
           }
         }
       }
       r += q.R;
     }
+    PROF_MARK(0);
+    PROF_DUMP(p, warp);
     if (lane == 0) tma_store_wait_all();   // outstanding bulk stores must land before exit
   }
 
@@ -338,7 +436,7 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kSlots * N >= 512 ? 512 : 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -346,7 +444,7 @@ template <int CO, int KC, int AS, bool BRES, int BP, int WST>
 int launch_uprow_variant(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const UprowParams& p, cudaStream_t st) {
   constexpr int N = 2 * CO;
   constexpr int smem = AS * KC * kPlaneStride + (BRES ? 9 * KC : WST * BP) * N * 128 + kEpiWarps * 2048 + 1024;
-  static_assert(smem + 3 * CO * 4 + 512 <= 227 * 1024, "shared memory budget");
+  static_assert(smem + 3 * CO * 4 + kNoiseSlots * 1024 + 512 <= 227 * 1024, "shared memory budget (dynamic + static)");
   auto kern = conv_tc_uprow_kernel<CO, KC, AS, BRES, BP, WST>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -384,12 +482,14 @@ __global__ void pack_uprow_weight_kernel(__nv_bfloat16* __restrict__ dst, const 
 int uprow_co(int Cin, int Cout) {
   if (Cin == 64 && Cout == 32) return 32;
   if (Cin == 128 && Cout == 64) return 64;
+  if (Cin == 256 && Cout == 128) return 64;   // two channel parts of 64
   return 0;
 }
 
 }  // namespace
 
-// Layers this kernel takes (bf16 inference, no saved activations): 64 -> 32 and 128 -> 64 up-convs on >= 128-wide inputs.
+// Layers this kernel takes (bf16 inference, no saved activations): 64 -> 32, 128 -> 64 and 256 -> 128 up-convs on inputs whose
+// width is a multiple of 128.
 bool conv_tc_uprow_supported(const ConvGeom& g, const EpiParams& e) {
   if (!g_switches.uprow || !tmap_available()) return false;
   if (g.up_cout <= 0 || uprow_co(g.Cin, g.up_cout) == 0) return false;
@@ -435,7 +535,16 @@ int launch_conv_tc_uprow(const void* in, const __nv_bfloat16* w, const ConvGeom&
     L2I_TRY(make_tmap_strided(&to, e.out, 4, dims, str, box, estr, CU_TENSOR_MAP_SWIZZLE_64B));
   }
   if (CO == 32) return launch_uprow_variant<32, 1, 4, true, 1, 1>(ta, tw, to, p, st);
-  return launch_uprow_variant<64, 2, 2, false, 2, 4>(ta, tw, to, p, st);
+  if (g.Cin == 128) return launch_uprow_variant<64, 2, 2, false, 2, 4>(ta, tw, to, p, st);
+  // Cin = 256: two input rows are 136 KB, which leaves a 4 x 16 KB weight ring (one 64-channel plane per stage)
+  return launch_uprow_variant<64, 4, 2, false, 1, 4>(ta, tw, to, p, st);
 }
 
 }  // namespace l2i
+
+#ifdef L2I_UPROW_PROF
+#include "generator_internal.cuh"
+extern "C" int l2i_debug_read_rgb_part(l2i_generator* g, void* dst, int64_t nbytes) {
+  return (int)cudaMemcpy(dst, g->rgb_part, (size_t)nbytes, cudaMemcpyDeviceToHost);
+}
+#endif

@@ -375,7 +375,10 @@ extern "C" int l2i_generator_mapping(l2i_generator_t* g, float* w, const float* 
   if (batch == 0) return L2I_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int D = g->D;
-  if (g->n_mlp > 0 && D % 4 == 0 && D <= 4096) {   // PixelNorm + every mapping layer in one launch
+  // PixelNorm + one batch-in-lanes linear launch per layer (weights read once per 32 latent rows; the single-launch fused kernel
+  // streams the 8 MB of weights once per ROW and took 0.23 ms at batch 32).  L2I_MAPPING_FUSED=1 selects the fused kernel.
+  static const bool fused_mapping = std::getenv("L2I_MAPPING_FUSED") != nullptr && std::atoi(std::getenv("L2I_MAPPING_FUSED")) != 0;
+  if (fused_mapping && g->n_mlp > 0 && D % 4 == 0 && D <= 4096) {
     const float ws = (1.0f / std::sqrt((float)D)) * g->lr_mlp;
     return launch_mapping_fused(w, z, g->map_w_ptrs, g->map_b_ptrs, batch, g->n_mlp, D, ws, g->lr_mlp, st);
   }
@@ -462,6 +465,7 @@ extern "C" int l2i_generator_forward(l2i_generator_t* g, const float* latent, in
       e.noise = nz; e.noise_bs = nz_bs; e.noise_w = nz_w;
       e.s_next = s_next; e.s_next_bs = g->s_rows;
       e.out = g->act[cur ^ 1];
+      e.rgb_part = g->rgb_part;   // scratch (only the cycle-accounting build of conv_tc_uprow.cu writes to it)
       const double px_in = (double)B * L.res_in * L.res_in, px_out = (double)B * L.res_out * L.res_out;
       auto* sg_c = g->seg_begin(L.name + "/upconv+blur_act", 0, 2.0 * 9 * L.cin * L.cout * px_in,
                                 (px_in * L.cin + px_out * L.cout) * es + px_out * 4.0, st);
@@ -554,7 +558,7 @@ extern "C" int l2i_generator_forward(l2i_generator_t* g, const float* latent, in
     g->seg_end(sg_u, st);
   }
   g->last_batch = B;
-  if (g->training) g->last_train_batch = B;
+  g->last_train_batch = g->training ? B : 0;   // any inference forward invalidates a pending backward (style tables / buffers reused)
   return L2I_OK;
 }
 

@@ -47,10 +47,101 @@ linear_kernel(float* __restrict__ y, int64_t y_stride, const float* __restrict__
   }
 }
 
+// Batch-in-lanes variant (the 26 modulation linears of a forward: ~7000 rows x 512 at B = 32; the walk MLPs):
+// lane = batch row, a warp owns 4 consecutive output rows, the input tile sits TRANSPOSED in shared memory ([K][32], so
+// lane b reads xs[k][b] without bank conflicts) and the weight row is a warp-uniform 16-byte load.  Per 4 k: 4 uniform LDG.128
+// + 4 LDS + 16 FMA, no cross-lane reduction, one 16-byte store per lane.  Weights are read once per 32 batch rows.
+// Requires the rows of one 4-row group to share row_xoff (true for the generator: every Cin is a multiple of 4).
+constexpr int kLinBtWarps = 8;
+__global__ void __launch_bounds__(kLinBtWarps * 32)
+linear_bt_kernel(float* __restrict__ y, int64_t y_stride, const float* __restrict__ x, int64_t x_stride,
+                 const int* __restrict__ row_xoff, const float* __restrict__ W, const float* __restrict__ bias,
+                 int B, int N, int K, float wscale, float bscale, int act, float alpha, float gain, int groups_per_block) {
+  extern __shared__ float xs[];   // [K][32]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b0 = blockIdx.y * 32;
+  const int g_begin = blockIdx.x * groups_per_block, g_end = min(g_begin + groups_per_block, (N + 3) / 4);
+  int staged_xoff = -1;
+  for (int gb = g_begin; gb < g_end; gb += kLinBtWarps) {
+    // all warps of the block walk the groups together so that a change of the input slice restages the tile once
+    const int g = gb + warp;
+    const int xoff_blk = row_xoff != nullptr ? row_xoff[min(gb * 4, N - 1)] : 0;
+    const int xoff_last = row_xoff != nullptr ? row_xoff[min((min(gb + kLinBtWarps, g_end)) * 4 - 1, N - 1)] : 0;
+    if (xoff_blk != staged_xoff) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < K * 32; i += blockDim.x) {
+        const int bb = i / K, k = i - bb * K;          // coalesced read of row bb, transposed write
+        xs[k * 32 + bb] = (b0 + bb < B) ? x[(int64_t)(b0 + bb) * x_stride + xoff_blk + k] : 0.f;
+      }
+      __syncthreads();
+      staged_xoff = xoff_blk;
+    }
+    if (g < g_end) {
+      const int n0 = g * 4;
+      const bool uniform = xoff_last == xoff_blk;       // the whole pass reads the staged slice
+      const int my_xoff = row_xoff != nullptr ? row_xoff[n0] : 0;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      if (uniform || my_xoff == staged_xoff) {
+        const float* w0 = W + (int64_t)min(n0, N - 1) * K;
+        const float* w1 = W + (int64_t)min(n0 + 1, N - 1) * K;
+        const float* w2 = W + (int64_t)min(n0 + 2, N - 1) * K;
+        const float* w3 = W + (int64_t)min(n0 + 3, N - 1) * K;
+#pragma unroll 4
+        for (int k = 0; k < K; k += 4) {   // 16 independent 16-byte weight loads in flight per lane (the loop is L2-latency bound)
+          const float4 a0 = __ldg(reinterpret_cast<const float4*>(w0 + k));
+          const float4 a1 = __ldg(reinterpret_cast<const float4*>(w1 + k));
+          const float4 a2 = __ldg(reinterpret_cast<const float4*>(w2 + k));
+          const float4 a3 = __ldg(reinterpret_cast<const float4*>(w3 + k));
+          const float x0 = xs[(k + 0) * 32 + lane], x1 = xs[(k + 1) * 32 + lane], x2 = xs[(k + 2) * 32 + lane], x3 = xs[(k + 3) * 32 + lane];
+          acc[0] = fmaf(a0.x, x0, fmaf(a0.y, x1, fmaf(a0.z, x2, fmaf(a0.w, x3, acc[0]))));
+          acc[1] = fmaf(a1.x, x0, fmaf(a1.y, x1, fmaf(a1.z, x2, fmaf(a1.w, x3, acc[1]))));
+          acc[2] = fmaf(a2.x, x0, fmaf(a2.y, x1, fmaf(a2.z, x2, fmaf(a2.w, x3, acc[2]))));
+          acc[3] = fmaf(a3.x, x0, fmaf(a3.y, x1, fmaf(a3.z, x2, fmaf(a3.w, x3, acc[3]))));
+        }
+      } else {
+        // a pass that straddles two input slices (never the case for the generator's tables): read x from global
+        for (int r = 0; r < 4; ++r) {
+          const int n = min(n0 + r, N - 1);
+          const int xo = row_xoff[n];
+          if (b0 + lane < B)
+            for (int k = 0; k < K; ++k) acc[r] = fmaf(W[(int64_t)n * K + k], x[(int64_t)(b0 + lane) * x_stride + xo + k], acc[r]);
+        }
+      }
+      if (b0 + lane < B) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          if (n0 + r >= N) break;
+          float v = acc[r] * wscale + (bias != nullptr ? bias[n0 + r] * bscale : 0.f);
+          if (act == 1) v = lrelu(v, alpha);
+          y[(int64_t)(b0 + lane) * y_stride + n0 + r] = v * gain;
+        }
+      }
+    }
+  }
+}
+
 int launch_linear(float* y, int64_t y_stride, const float* x, int64_t x_stride, const int* row_xoff,
                   const float* W, const float* bias, int B, int N, int K, float wscale, float bscale,
                   int act, float alpha, float gain, cudaStream_t st) {
   if (B == 0 || N == 0) return L2I_OK;
+  const size_t bt_smem = (size_t)K * 32 * sizeof(float);
+  // taken for EVERY batch size (not only the large ones): the summation order must not depend on the batch, image i of a
+  // batch is bit-identical to the same latent run alone (tests/test_gpu_generator.py::test_large_batch_matches_single_sample_runs)
+  if (K % 4 == 0 && bt_smem <= 96 * 1024 && ((uintptr_t)W % 16 == 0)) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      L2I_CUDA_TRY(cudaFuncSetAttribute(linear_bt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr_set = true;
+    }
+    const int groups = (N + 3) / 4;
+    // enough blocks to fill the machine, each a multiple of kLinBtWarps groups so a block restages x as rarely as possible
+    const int target_blocks = std::max(1, 2 * kNumSMs / ceil_div(B, 32));
+    const int gpb = ceil_div(ceil_div(groups, target_blocks), kLinBtWarps) * kLinBtWarps;
+    dim3 grid(ceil_div(groups, gpb), ceil_div(B, 32));
+    linear_bt_kernel<<<grid, kLinBtWarps * 32, bt_smem, st>>>(y, y_stride, x, x_stride, row_xoff, W, bias, B, N, K, wscale, bscale,
+                                                               act, alpha, gain, gpb);
+    return check_launch("linear_bt");
+  }
   dim3 grid(ceil_div(N, kLinRowsPerBlock), std::min(ceil_div(B, kLinBatchTile), 64));
   linear_kernel<<<grid, kLinRowsPerBlock * 32, 0, st>>>(y, y_stride, x, x_stride, row_xoff, W, bias, B, N, K,
                                                         wscale, bscale, act, alpha, gain);
@@ -198,6 +289,101 @@ walk_combine_kernel(float* __restrict__ out, const float* __restrict__ in, int64
   }
 }
 
+
+// ---- backward of the fused linear (walk MLP training; transform_base.py:175-179, 214-217 under autograd) ----------------
+// g = gy * act'(y) is formed on the fly from the saved OUTPUT's sign (leaky relu: y > 0 <=> pre-activation > 0).
+__device__ __forceinline__ float lin_g(const float* __restrict__ gy, const float* __restrict__ y, int64_t i, int act, float alpha) {
+  const float g = gy[i];
+  return (act == 1 && y[i] <= 0.f) ? g * alpha : g;
+}
+
+// gx[b, k] = sum_n g[b, n] W[n, k]: one thread per k (coalesced weight rows), kLinBatchTile batch rows per block
+__global__ void __launch_bounds__(128)
+linear_bwd_x_kernel(float* __restrict__ gx, const float* __restrict__ gy, const float* __restrict__ y,
+                    const float* __restrict__ W, int B, int N, int K, int act, float alpha) {
+  extern __shared__ float gs[];   // [kLinBatchTile][N]
+  const int b0 = blockIdx.y * kLinBatchTile;
+  for (int i = threadIdx.x; i < kLinBatchTile * N; i += blockDim.x) {
+    const int j = i / N, n = i - j * N;
+    gs[i] = (b0 + j < B) ? lin_g(gy, y, (int64_t)(b0 + j) * N + n, act, alpha) : 0.f;
+  }
+  __syncthreads();
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float acc[kLinBatchTile];
+#pragma unroll
+  for (int j = 0; j < kLinBatchTile; ++j) acc[j] = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const float w = W[(int64_t)n * K + k];
+#pragma unroll
+    for (int j = 0; j < kLinBatchTile; ++j) acc[j] = fmaf(gs[j * N + n], w, acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < kLinBatchTile; ++j)
+    if (b0 + j < B) gx[(int64_t)(b0 + j) * K + k] = acc[j];
+}
+
+// gW[n, k] = sum_b g[b, n] x[b, k];  gb[n] = sum_b g[b, n]: one block per n, threads over k
+__global__ void __launch_bounds__(256)
+linear_bwd_w_kernel(float* __restrict__ gW, float* __restrict__ gb, const float* __restrict__ gy, const float* __restrict__ y,
+                    const float* __restrict__ x, int B, int N, int K, int act, float alpha) {
+  const int n = blockIdx.x;
+  float bsum = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc = fmaf(lin_g(gy, y, (int64_t)b * N + n, act, alpha), x[(int64_t)b * K + k], acc);
+    gW[(int64_t)n * K + k] = acc;
+  }
+  if (gb != nullptr && threadIdx.x == 0) {
+    for (int b = 0; b < B; ++b) bsum += lin_g(gy, y, (int64_t)b * N + n, act, alpha);
+    gb[n] = bsum;
+  }
+}
+
+// Gradient of walk_combine w.r.t. d (one block per (layer, sample)); with d_ls == 0 (one MLP output serves every layer)
+// the per-layer contributions are summed by the caller's second kernel below.
+//   out = in + c * d            : gd = c * g
+//   out = in + d / ||d||        : gd = (g - <g, u> u) / ||d||,  u = d / ||d||
+__global__ void __launch_bounds__(128)
+walk_combine_bwd_kernel(float* __restrict__ gd, const float* __restrict__ g, const float* __restrict__ d, int64_t d_bs,
+                        int64_t d_ls, const float* __restrict__ coef, int n_latent, int D, uint64_t mask, int normalize) {
+  const int i = blockIdx.x, b = blockIdx.y;
+  const bool on = (mask >> i) & 1ull;
+  const float* dr = d + (int64_t)b * d_bs + (int64_t)i * d_ls;
+  const float* gr = g + ((int64_t)b * n_latent + i) * D;
+  float* o = gd + ((int64_t)b * n_latent + i) * D;
+  const float c = coef != nullptr ? coef[b] : 1.f;
+  __shared__ float red[2][4];
+  float inv = 1.f, dot = 0.f;
+  if (on && normalize) {
+    float s = 0.f, t = 0.f;
+    for (int k = threadIdx.x; k < D; k += blockDim.x) { s += dr[k] * dr[k]; t += gr[k] * dr[k]; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, off); t += __shfl_xor_sync(0xffffffffu, t, off); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = t; }
+    __syncthreads();
+    const float nn = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+    inv = 1.f / sqrtf(nn);
+    dot = (red[1][0] + red[1][1] + red[1][2] + red[1][3]) / nn;      // <g, d> / ||d||^2
+  }
+  for (int k = threadIdx.x; k < D; k += blockDim.x) {
+    float v = 0.f;
+    if (on) v = normalize ? c * inv * (gr[k] - dot * dr[k]) : c * gr[k];
+    o[k] = v;
+  }
+}
+
+// gd_shared[b, :] = sum_i gd[b, i, :]
+__global__ void __launch_bounds__(128)
+layer_sum_kernel(float* __restrict__ out, const float* __restrict__ in, int n_latent, int D) {
+  const int b = blockIdx.x;
+  for (int k = threadIdx.x; k < D; k += blockDim.x) {
+    float s = 0.f;
+    for (int i = 0; i < n_latent; ++i) s += in[((int64_t)b * n_latent + i) * D + k];
+    out[(int64_t)b * D + k] = s;
+  }
+}
+
 }  // namespace l2i
 
 using namespace l2i;
@@ -252,4 +438,43 @@ extern "C" int l2i_walk_combine(float* out, const float* in, int64_t in_batch_st
       out, in, in_batch_stride, in_layer_stride, d, d_batch_stride, d_layer_stride, coef, n_latent, D,
       layer_mask, normalize);
   return check_launch("walk_combine");
+}
+
+extern "C" int l2i_linear_bwd(float* gx, float* gW, float* gb, const float* gy, const float* y, const float* x, const float* W,
+                              int B, int N, int K, int act, float alpha, void* stream) {
+  L2I_REQUIRE(B >= 0 && N >= 1 && K >= 1, "linear_bwd: bad shape");
+  L2I_REQUIRE(act == 0 || act == 1, "linear_bwd: act must be 0 or 1");
+  if (B == 0) return L2I_OK;
+  L2I_REQUIRE(gy && x && W && (act == 0 || y), "linear_bwd: null tensor");
+  L2I_REQUIRE((size_t)kLinBatchTile * N * sizeof(float) <= 48 * 1024, "linear_bwd: N = %d too large for the staged gradient tile", N);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (gx != nullptr) {
+    linear_bwd_x_kernel<<<dim3(ceil_div(K, 128), ceil_div(B, kLinBatchTile)), 128, kLinBatchTile * N * sizeof(float), st>>>(
+        gx, gy, y, W, B, N, K, act, alpha);
+    L2I_TRY(check_launch("linear_bwd_x"));
+  }
+  if (gW != nullptr) {
+    linear_bwd_w_kernel<<<N, 256, 0, st>>>(gW, gb, gy, y, x, B, N, K, act, alpha);
+    L2I_TRY(check_launch("linear_bwd_w"));
+  }
+  return L2I_OK;
+}
+
+extern "C" int l2i_walk_combine_bwd(float* grad_d, float* scratch, const float* grad_out, const float* d, int64_t d_batch_stride,
+                                    int64_t d_layer_stride, const float* coef, int B, int n_latent, int D, uint64_t layer_mask,
+                                    int normalize, void* stream) {
+  L2I_REQUIRE(B >= 0 && n_latent >= 1 && n_latent <= 64 && D >= 1, "walk_combine_bwd: bad shape");
+  if (B == 0) return L2I_OK;
+  L2I_REQUIRE(grad_d && grad_out && d, "walk_combine_bwd: null tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool shared = d_layer_stride == 0;
+  L2I_REQUIRE(!shared || scratch != nullptr, "walk_combine_bwd: shared d needs a [B, n_latent, D] scratch buffer");
+  walk_combine_bwd_kernel<<<dim3(n_latent, B), 128, 0, st>>>(shared ? scratch : grad_d, grad_out, d, d_batch_stride, d_layer_stride,
+                                                            coef, n_latent, D, layer_mask, normalize);
+  L2I_TRY(check_launch("walk_combine_bwd"));
+  if (shared) {
+    layer_sum_kernel<<<B, 128, 0, st>>>(grad_d, scratch, n_latent, D);
+    L2I_TRY(check_launch("walk_combine_bwd_sum"));
+  }
+  return L2I_OK;
 }

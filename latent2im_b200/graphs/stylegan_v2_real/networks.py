@@ -195,8 +195,8 @@ class _SynthesisFn(torch.autograd.Function):
     def backward(ctx, grad_image):
         gen = ctx.gen
         if gen._last_train is not ctx.token:
-            raise RuntimeError("Generator backward: another training-mode forward ran before this backward; "
-                               "the native library keeps the activations of one forward at a time")
+            raise RuntimeError("Generator backward: another forward (training or inference) ran on this generator before this "
+                               "backward; the native library keeps the activations and style tables of one forward at a time")
         h, batch, _ = ctx.token
         g = grad_image.contiguous().float()
         grad_latent = torch.empty(ctx.lat_shape, device=g.device, dtype=torch.float32)
@@ -388,6 +388,10 @@ class Generator(nn.Module):
                      "generator_forward")
         if training:
             self._last_train = (h, batch, nz)  # the noise tensors must outlive the backward pass
+        elif getattr(self, "_last_train", None) is not None and self._last_train[0] is h:
+            # an inference forward on the SAME native handle rewrote its style / demod tables and activation buffers: the
+            # pending backward of the earlier training forward would silently mix them with its saved activations
+            self._last_train = None
         self._last = (h, batch, nz)  # keeps the noise tensors alive until the next call
         if want_uint8 and want_float:
             return image, image_u8

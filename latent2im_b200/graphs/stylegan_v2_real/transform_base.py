@@ -104,7 +104,7 @@ class _WalkLinearFn(Function):
 
 
 class _LinearFn(Function):
-    """y = act(x W^T + b) through l2i_linear_fwd; backward reuses the same kernel on transposed operands."""
+    """y = act(x W^T + b) through l2i_linear_fwd; backward (gx, gW, gb, activation derivative) through l2i_linear_bwd."""
 
     @staticmethod
     def forward(ctx, x, W, b, act):
@@ -124,27 +124,18 @@ class _LinearFn(Function):
     @staticmethod
     def backward(ctx, gy):
         x2, Wc, y = ctx.saved_tensors
-        lib = nt.load()
         g = gy.contiguous().float()
         B, K = x2.shape
         N = Wc.shape[0]
         dev = g.device
-        with torch.cuda.device(dev):
-            st = nt.stream_ptr(dev)
-            if ctx.act:  # leaky relu derivative from the saved output's sign
-                g2 = torch.empty_like(g)
-                nt.check(lib.l2i_fused_bias_act(g2.data_ptr(), g.data_ptr(), None, y.data_ptr(), g.numel(), 1, 0, 3, 1, 0.2, 1.0,
-                                                nt.F32, st), "fused_bias_act")
-                g = g2
-            gx = torch.empty(B, K, device=dev, dtype=torch.float32)
-            Wt = Wc.t().contiguous()
-            nt.check(lib.l2i_linear_fwd(gx.data_ptr(), K, g.data_ptr(), N, Wt.data_ptr(), None, B, K, N, 1.0, 0.0, 0, 0.0, 1.0, st),
-                     "linear_bwd_x")
-            gW = torch.empty(N, K, device=dev, dtype=torch.float32)
-            gt, xt = g.t().contiguous(), x2.t().contiguous()
-            nt.check(lib.l2i_linear_fwd(gW.data_ptr(), K, gt.data_ptr(), B, xt.data_ptr(), None, N, K, B, 1.0, 0.0, 0, 0.0, 1.0, st),
-                     "linear_bwd_w")
-        return gx, gW, g.sum(0), None
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        gx = torch.empty(B, K, device=dev, dtype=torch.float32) if need_x else None
+        gW = torch.empty(N, K, device=dev, dtype=torch.float32) if need_w else None
+        gb = torch.empty(N, device=dev, dtype=torch.float32) if need_w else None
+        with torch.cuda.device(dev):   # leaky-relu derivative (from the saved output's sign), gx, gW and gb in two native launches
+            nt.check(nt.load().l2i_linear_bwd(nt.ptr(gx), nt.ptr(gW), nt.ptr(gb), g.data_ptr(), y.data_ptr(), x2.data_ptr(),
+                                              Wc.data_ptr(), B, N, K, 1 if ctx.act else 0, 0.2, nt.stream_ptr(dev)), "linear_bwd")
+        return gx, gW, gb, None
 
 
 def _mlp(seq, x):
@@ -156,39 +147,56 @@ def _mlp(seq, x):
     return x
 
 
+class _CombineFn(Function):
+    """out_i = in_i + coef * d_i (or in_i + d_i / ||d_i||) through l2i_walk_combine / l2i_walk_combine_bwd: the MLP walks
+    train through native kernels only (the reference differentiates torch ops, transform_base.py:188-193, 227-229)."""
+
+    @staticmethod
+    def forward(ctx, dblk, coef, mask, normalize, shared_d, n, *ws):
+        blk, bs, ls = _as_latent_block(ws)
+        B, D = ws[0].shape
+        d = dblk.detach().float().contiguous()
+        dbs, dls = (d.stride(0), 0) if shared_d else (d.stride(0), d.stride(1))
+        c = coef.detach().float().reshape(-1).contiguous() if coef is not None else None
+        out = torch.empty(B, n, D, device=blk.device, dtype=torch.float32)
+        with torch.cuda.device(blk.device):
+            nt.check(nt.load().l2i_walk_combine(out.data_ptr(), blk.data_ptr(), bs, ls, d.data_ptr(), dbs, dls, nt.ptr(c), B, n, D,
+                                                mask, 1 if normalize else 0, nt.stream_ptr(blk.device)), "walk_combine")
+        ctx.save_for_backward(d, c) if c is not None else ctx.save_for_backward(d)
+        ctx.cfg = (mask, normalize, shared_d, n, D, dbs, dls, c is not None, len(ws))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        mask, normalize, shared_d, n, D, dbs, dls, has_c, n_in = ctx.cfg
+        saved = ctx.saved_tensors
+        d, c = saved[0], (saved[1] if has_c else None)
+        g = grad_out.contiguous().float()
+        B = g.shape[0]
+        gd = None
+        if ctx.needs_input_grad[0]:
+            gd = torch.empty_like(d)
+            scratch = torch.empty(B, n, D, device=g.device, dtype=torch.float32) if shared_d else None
+            with torch.cuda.device(g.device):
+                nt.check(nt.load().l2i_walk_combine_bwd(gd.data_ptr(), nt.ptr(scratch), g.data_ptr(), d.data_ptr(), dbs, dls,
+                                                        nt.ptr(c), B, n, D, mask, 1 if normalize else 0,
+                                                        nt.stream_ptr(g.device)), "walk_combine_bwd")
+        # d out_i / d in_i = I; the step size (alpha) is a value on the training path, never a parameter
+        gins = tuple(g[:, i] if ctx.needs_input_grad[6 + i] else None for i in range(n_in))
+        return (gd, None, None, None, None, None) + gins
+
+
 def _combine(ws, d_list, coef, mask, normalize):
-    """out_i = in_i + coef * d_i (or in_i + d_i/||d_i||); differentiable through torch ops on the
-    small [B, D] tensors only when grad is needed, native kernel otherwise."""
+    """out_i = in_i + coef * d_i (or in_i + d_i/||d_i||) for the layers in `mask`: one native launch forward, one or two
+    backward, with or without grad."""
     n = len(ws)
     fill = next((t for t in d_list if t is not None), None)
     if fill is None:
         return list(ws)
     d_list = [fill if t is None else t for t in d_list]
-    need_grad = torch.is_grad_enabled() and any(t.requires_grad for t in d_list)
-    if need_grad:
-        out = []
-        for i in range(n):
-            if (mask >> i) & 1:
-                d = d_list[i]
-                if normalize:
-                    d = d / torch.norm(d, dim=1, keepdim=True)
-                out.append(ws[i] + (coef * d if coef is not None else d))
-            else:
-                out.append(ws[i])
-        return out
-    blk, bs, ls = _as_latent_block(ws)
-    B, D = ws[0].shape
-    if all(t is d_list[0] for t in d_list):
-        dblk = d_list[0].detach().float().contiguous()
-        dbs, dls = dblk.stride(0), 0
-    else:
-        dblk = torch.stack([t.detach().float() for t in d_list], 1).contiguous()
-        dbs, dls = dblk.stride(0), dblk.stride(1)
-    c = coef.detach().float().reshape(-1).contiguous() if coef is not None else None
-    out = torch.empty(B, n, D, device=blk.device, dtype=torch.float32)
-    with torch.cuda.device(blk.device):
-        nt.check(nt.load().l2i_walk_combine(out.data_ptr(), blk.data_ptr(), bs, ls, dblk.data_ptr(), dbs, dls, nt.ptr(c), B, n, D,
-                                            mask, 1 if normalize else 0, nt.stream_ptr(blk.device)), "walk_combine")
+    shared = all(t is d_list[0] for t in d_list)
+    dblk = d_list[0] if shared else torch.stack(list(d_list), 1)
+    out = _CombineFn.apply(dblk, coef, mask, bool(normalize), shared, n, *ws)
     return list(out.unbind(1))
 
 
@@ -208,6 +216,11 @@ class WalkLinearMultiW(nn.Module):
     def forward(self, input, alpha, layers=None, name=None, index_=None):
         n = len(input)
         alpha = alpha.to(input[0].device)
+        # the kernel indexes w as [A][n][D] from raw pointers: a walk trained for another resolution (n_latent) or attribute
+        # count must fail here, like the reference's `self.w[:, i, :]` / `alpha @ w` would (IndexError / shape error)
+        if alpha.ndim != 2 or tuple(self.w.shape) != (alpha.shape[1], n, input[0].shape[1]):
+            raise RuntimeError(f"WalkLinearMultiW: walk parameter {tuple(self.w.shape)} does not match alpha {tuple(alpha.shape)}, "
+                               f"{n} latent layers of width {input[0].shape[1]} (expected w = [A, n_latent, D])")
         out = _WalkLinearFn.apply(self.w, alpha, _layer_mask(n, layers), n, *input)
         return list(out.unbind(1))
 

@@ -379,3 +379,27 @@ def test_uprow_fused_upconv_matches_oracle(batch, monkeypatch):
         assert rel <= 2e-2, (name, rel.item())
     assert _psnr(imgs["1"].cpu().double(), ref) >= 45.0
     assert _psnr(imgs["1"].double(), imgs["0"].double()) >= 46.0
+
+
+def test_forward_between_training_forward_and_backward_is_rejected():
+    """The native handle keeps ONE forward's activations and style tables: a second forward (training OR a no-grad
+    preview render) before the backward must make that backward fail loudly instead of returning mixed gradients."""
+    gen, sd, spec = _build(16, 32, 1)
+    gen.set_native(dtype=torch.float32)
+    noise = [n.cuda() for n in synthetic_noise(spec.num_layers, 2)]
+    for second_requires_grad in (False, True):
+        lat = _latent(spec, 2).cuda().requires_grad_(True)
+        img, _ = gen(lat, input_is_latent=True, noise=noise)
+        other = _latent(spec, 2, seed=5).cuda().requires_grad_(second_requires_grad)
+        if second_requires_grad:
+            gen(other, input_is_latent=True, noise=noise)
+        else:
+            with torch.no_grad():
+                gen(other, input_is_latent=True, noise=noise)
+        with pytest.raises(RuntimeError, match="before this backward"):
+            img.sum().backward()
+    # and the normal order still works
+    lat = _latent(spec, 2).cuda().requires_grad_(True)
+    img, _ = gen(lat, input_is_latent=True, noise=noise)
+    img.sum().backward()
+    assert torch.isfinite(lat.grad).all()

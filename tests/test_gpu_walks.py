@@ -89,6 +89,80 @@ def test_walk_nonlinear_forward():
         assert torch.allclose(a.cpu().double(), b, atol=1e-4)
 
 
+@pytest.mark.parametrize("shared", [True, False])
+@pytest.mark.parametrize("layers", [None, [0, 2]])
+def test_walk_nonlinear_gradients(shared, layers):
+    """Training path of WalkNonLinearW (embed -> MLP -> d / ||d|| -> add) runs on l2i_linear_fwd/bwd and
+    l2i_walk_combine/_bwd only; parameter AND input-latent gradients vs float64 autograd through the oracle
+    (transform_base.py:219-243).  layers=None normalises d, a layer list does not (reference behaviour)."""
+    tb = _mods()
+    torch.manual_seed(3)
+    walk = tb.WalkNonLinearW(32, 1, 1, ["a"]).cuda()
+    B, n = 5, 4
+    base = torch.randn(B, 32, device="cuda")
+    ws = [base.clone().requires_grad_(True)] * n if shared else [torch.randn(B, 32, device="cuda").requires_grad_(True) for _ in range(n)]
+    alpha = torch.randn(B, 1, device="cuda")
+    probe = torch.randn(B, n, 32, device="cuda")
+    out = walk(ws, alpha=alpha, layers=layers)
+    (torch.stack(out, 1) * probe).sum().backward()
+
+    emb = tuple(t.detach().cpu().double().requires_grad_(True) for t in (walk.embed.weight, walk.embed.bias))
+    pr = [(w.clone().requires_grad_(True), b.clone().requires_grad_(True)) for w, b in _seq_params(walk.linear)]
+    if shared:
+        b64 = ws[0].detach().cpu().double().requires_grad_(True)
+        ws64 = [b64] * n
+    else:
+        ws64 = [w.detach().cpu().double().requires_grad_(True) for w in ws]
+    ref = walk_nonlinear_ref(ws64, alpha.cpu().double(), emb, pr, layers=layers)
+    (torch.stack(ref, 1) * probe.cpu().double()).sum().backward()
+    for a, b in zip(out, ref):
+        assert torch.allclose(a.detach().cpu().double(), b.detach(), atol=1e-4)
+    lin = [m for m in walk.linear if isinstance(m, torch.nn.Linear)]
+    for m, (w, b) in zip([walk.embed] + lin, [emb] + pr):
+        assert torch.allclose(m.weight.grad.cpu().double(), w.grad, atol=2e-3, rtol=2e-3), m
+        assert torch.allclose(m.bias.grad.cpu().double(), b.grad, atol=2e-3, rtol=2e-3), m
+    got_in = [ws[0].grad] if shared else [w.grad for w in ws]
+    ref_in = [ws64[0].grad] if shared else [w.grad for w in ws64]
+    for a, b in zip(got_in, ref_in):
+        assert torch.allclose(a.cpu().double(), b, atol=2e-3, rtol=2e-3)
+
+
+def test_walk_mlp_gradients_distinct_inputs_and_layers():
+    """WalkMlpMultiW with a genuinely per-layer W+ list (one MLP evaluation per layer, stacked d) restricted to two layers."""
+    tb = _mods()
+    torch.manual_seed(4)
+    walk = tb.WalkMlpMultiW(32, 1, 1, ["a"]).cuda()
+    B, n = 3, 4
+    ws = [torch.randn(B, 32, device="cuda").requires_grad_(True) for _ in range(n)]
+    alpha = torch.randn(B, 1, device="cuda")
+    probe = torch.randn(B, n, 32, device="cuda")
+    out = walk(ws, alpha, layers=[1, 3])
+    (torch.stack(out, 1) * probe).sum().backward()
+    pr = [(w.clone().requires_grad_(True), b.clone().requires_grad_(True)) for w, b in _seq_params(walk.linear)]
+    ws64 = [w.detach().cpu().double().requires_grad_(True) for w in ws]
+    ref = walk_mlp_ref(ws64, alpha.cpu().double(), pr, layers=[1, 3])
+    (torch.stack(ref, 1) * probe.cpu().double()).sum().backward()
+    lin = [m for m in walk.linear if isinstance(m, torch.nn.Linear)]
+    for m, (w, b) in zip(lin, pr):
+        assert torch.allclose(m.weight.grad.cpu().double(), w.grad, atol=1e-3, rtol=1e-3)
+        assert torch.allclose(m.bias.grad.cpu().double(), b.grad, atol=1e-3, rtol=1e-3)
+    for a, b in zip(ws, ws64):
+        assert torch.allclose(a.grad.cpu().double(), b.grad, atol=1e-3, rtol=1e-3)
+
+
+def test_walk_linear_rejects_mismatched_parameter_shape():
+    """A walk trained for 14 latent layers applied to an 18-layer W+ list (or alpha with the wrong attribute count) must
+    raise, not read past the parameter buffer."""
+    tb = _mods()
+    np.random.seed(0)
+    walk = tb.WalkLinearMultiW(64, 2, 1, ["a", "b"]).cuda()       # w: [2, 6, 64]
+    base = torch.randn(3, 64, device="cuda")
+    with pytest.raises(RuntimeError, match="does not match"):
+        walk([base] * 8, torch.randn(3, 2, device="cuda"))
+    with pytest.raises(RuntimeError, match="does not match"):
+        walk([base] * 6, torch.randn(3, 3, device="cuda"))
+
+
 def test_walk_pickle_roundtrip_under_reference_module_path(tmp_path):
     import latent2im_b200
     latent2im_b200.install_dropin()

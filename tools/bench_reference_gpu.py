@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--ref-only", action="store_true", help="time only the reference (bench.py's ref_gpu_baseline key)")
     a = ap.parse_args()
     if not os.path.isdir(os.path.join(REF, "graphs")):
         print(json.dumps({"impl": "reference_gpu", "unavailable": "baseline/_ref not staged (run oracle/stage_reference.py)"}))
@@ -76,6 +77,8 @@ def main():
                 out["fp32_tf32_on" if tf32 else "fp32_tf32_off"] = {"error": str(e)[:200]}
                 torch.cuda.empty_cache()
         try:
+            if a.ref_only:
+                raise RuntimeError("skipped (--ref-only)")
             ref16, lat16 = ref.half(), lat.half()
             ms = timed(lambda: ref16(lat16, input_is_latent=True), a.steps, a.warmup)
             out["fp16"] = {"ms_per_step": ms, "images_per_s": a.batch / ms * 1e3}
@@ -84,6 +87,9 @@ def main():
         del ref
         torch.cuda.empty_cache()
 
+        if a.ref_only:
+            print(json.dumps(out), flush=True)
+            return
         # this repository, same weights / latents / fresh noise, device-resident
         gen = Generator(a.size, 512, 8)
         gen.load_state_dict(sd, strict=False)
