@@ -136,34 +136,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer: warp-uniform control flow, one elected lane issues (tc_ptx.cuh: elect_one) =============
+    {
       int stage = 0;
       uint32_t phase_bit = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t smem0 = smem_u32(smem);
+      constexpr uint64_t kHi = kmajor_desc_hi(kSBO, kLayoutType);
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int ph, x0, y0, b, nt;
         decode(tile, ph, x0, y0, b, nt);
         const int nk = p.taps[ph].n * kchunks;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+        const uint32_t tmem_d = tmem_u + (uint32_t)(acc * BLOCK_N);
         for (int kb = 0; kb < nk; ++kb) {
           mbar_wait(&full_bar[stage], phase_bit);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
-          const uint32_t sb = sa + L::kABytes;
+          const uint32_t sa = smem0 + (uint32_t)(stage * L::kStageBytes);
+          const uint64_t a_desc = kmajor_desc_at(kHi, sa), b_desc = kmajor_desc_at(kHi, sa + L::kABytes);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            const uint64_t adesc = make_kmajor_desc(sa + k * 32, kSBO, kLayoutType);
-            const uint64_t bdesc = make_kmajor_desc(sb + k * 32, kSBO, kLayoutType);
-            umma_bf16(tmem_d, adesc, bdesc, p.idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / 16; ++k)
+              umma_bf16(tmem_d, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), p.idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs have read it
           }
-          umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase_bit ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);      // accumulator complete
+        if (elect_one()) umma_commit(&tmem_full[acc]);      // accumulator complete
         if (++acc == GROUPS) { acc = 0; acc_phase ^= 1; }
       }
     }

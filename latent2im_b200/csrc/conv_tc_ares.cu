@@ -133,37 +133,45 @@ conv_tc_ares_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer: warp-uniform control flow, one elected lane issues (tc_ptx.cuh: elect_one) =============
+    {
       int stage = 0, ws = 0, grp = 0;
       uint32_t phase_bit = 0, wphase = 0, grp_phase = 0;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t smem_a0 = smem_u32(smem), smem_b0 = smem_u32(smem_b);
+      constexpr uint64_t kHiA = kmajor_desc_hi(kRW * 128, 2), kHiB = kmajor_desc_hi(1024, 2);
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty[grp], grp_phase ^ 1);
         mbar_wait(&a_full[stage], phase_bit);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + stage * kAStageBytes);
-        const uint32_t tmem_d = tmem_base + (uint32_t)(grp * N);
+        const uint32_t a_base = smem_a0 + (uint32_t)(stage * kAStageBytes);
+        const uint32_t tmem_d = tmem_u + (uint32_t)(grp * N);
+#pragma unroll 1
         for (int t = 0; t < 9; ++t) {
           const uint32_t shift = (uint32_t)(((t / 3) * kRW + (t % 3)) * 128);   // tap (dy, dx) = (t/3 - 1, t%3 - 1)
 #pragma unroll
           for (int kc = 0; kc < KC; kc += BP) {
             mbar_wait(&w_full[ws], wphase);
             tc_fence_after();
+            const uint64_t a_desc = kmajor_desc_at(kHiA, a_base + (uint32_t)(kc * kRPlaneStride) + shift);
+            const uint64_t b_desc = kmajor_desc_at(kHiB, smem_b0 + (uint32_t)(ws * kBStageBytes));
+            if (elect_one()) {
 #pragma unroll
-            for (int j = 0; j < BP; ++j) {
-              const uint32_t a_tap = a_base + (uint32_t)((kc + j) * kRPlaneStride) + shift;
-              const uint32_t b_tile = smem_u32(smem_b + ws * kBStageBytes + j * kBPlaneBytes);
+              for (int j = 0; j < BP; ++j) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(tmem_d, ares_desc(a_tap + k * 32, kRW * 128), ares_desc(b_tile + k * 32, 1024), p.idesc,
-                          (t | kc | j | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(tmem_d, a_desc + (uint64_t)((j * kRPlaneStride + k * 32) >> 4), b_desc + (uint64_t)((j * kBPlaneBytes + k * 32) >> 4),
+                            p.idesc, (t | kc | j | k) != 0 ? 1u : 0u);
+              }
+              umma_commit(&w_empty[ws]);
             }
-            umma_commit(&w_empty[ws]);
             if (++ws == WST) { ws = 0; wphase ^= 1; }
           }
         }
-        umma_commit(&a_empty[stage]);
-        umma_commit(&tmem_full[grp]);
+        if (elect_one()) {
+          umma_commit(&a_empty[stage]);
+          umma_commit(&tmem_full[grp]);
+        }
         if (++stage == kRAStages) { stage = 0; phase_bit ^= 1; }
         if (++grp == GROUPS) { grp = 0; grp_phase ^= 1; }
       }

@@ -149,11 +149,14 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer: warp-uniform control flow, one elected lane issues (tc_ptx.cuh: elect_one) =============
+    {
       mbar_wait(&w_bar, 0);
       tc_fence_after();
-      const uint32_t w_base = smem_u32(smem_w);
+      const uint32_t w_base = smem_u32(smem_w), smem_a0 = smem_u32(smem);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      constexpr uint64_t kHiA = kmajor_desc_hi(kHaloW * 128, 2), kHiB = kmajor_desc_hi(1024, 2);
+      const uint64_t b_desc0 = kmajor_desc_at(kHiB, w_base);
       int stage = 0;
       uint32_t phase_bit = 0;
       int grp = 0;
@@ -162,24 +165,24 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         mbar_wait(&tmem_empty[grp], grp_phase ^ 1);
         mbar_wait(&full_bar[stage], phase_bit);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + stage * kStageBytes);
-        const uint32_t tmem_d = tmem_base + (uint32_t)(grp * NACC * N);
-        uint32_t started = 0;  // accumulators that already received their first MMA
-        for (int t = 0; t < p.ntaps; ++t) {
-          const HaloTap tap = p.taps[t];
-          const uint32_t a_tap = a_base + (uint32_t)(((tap.dy + 1) * kHaloW + (tap.dx + 1)) * 128);
-          const uint32_t b_tap = w_base + (uint32_t)(tap.wtile * kWTileBytes);
-          const uint32_t boff = p.base_offset_mode ? ((a_tap >> 7) & 7u) : 0u;
+        const uint32_t a_base = smem_a0 + (uint32_t)(stage * kStageBytes);
+        const uint32_t tmem_d = tmem_u + (uint32_t)(grp * NACC * N);
+        if (elect_one()) {
+          uint32_t started = 0;  // accumulators that already received their first MMA
+          for (int t = 0; t < p.ntaps; ++t) {
+            const HaloTap tap = p.taps[t];
+            const uint32_t a_tap = a_base + (uint32_t)(((tap.dy + 1) * kHaloW + (tap.dx + 1)) * 128);
+            const uint64_t a_desc = kmajor_desc_at(kHiA, a_tap) | ((uint64_t)(p.base_offset_mode ? ((a_tap >> 7) & 7u) : 0u) << 49);
+            const uint64_t b_desc = b_desc0 + (uint64_t)((uint32_t)(tap.wtile * kWTileBytes) >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t adesc = make_desc_sw128(a_tap + k * 32, kHaloW * 128, boff);
-            const uint64_t bdesc = make_desc_sw128(b_tap + k * 32, 1024, 0);
-            umma_bf16(tmem_d + (uint32_t)(tap.acc * N), adesc, bdesc, p.idesc, ((started >> tap.acc) & 1u) | (k != 0 ? 1u : 0u));
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_d + (uint32_t)(tap.acc * N), a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), p.idesc,
+                        ((started >> tap.acc) & 1u) | (k != 0 ? 1u : 0u));
+            started |= 1u << tap.acc;
           }
-          started |= 1u << tap.acc;
+          umma_commit(&empty_bar[stage]);
+          umma_commit(&tmem_full[grp]);
         }
-        umma_commit(&empty_bar[stage]);
-        umma_commit(&tmem_full[grp]);
         if (++stage == STAGES) { stage = 0; phase_bit ^= 1; }
         if (++grp == kGroups) { grp = 0; grp_phase ^= 1; }
       }

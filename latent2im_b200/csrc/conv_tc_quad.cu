@@ -140,10 +140,14 @@ conv_tc_quad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (warp == 1) {
     // ===================== MMA issuer: 4 patch rows x 8 K16 steps, one N = 128 accumulator per tile =====
-    if (lane == 0) {
+    // warp-uniform control flow, one elected lane issues (tc_ptx.cuh: elect_one)
+    {
       mbar_wait(&w_bar, 0);
       tc_fence_after();
-      const uint32_t w_base = smem_u32(smem_w);
+      const uint32_t w_base = smem_u32(smem_w), smem_a0 = smem_u32(smem);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      constexpr uint64_t kHiA = kmajor_desc_hi(2 * kQRowPitch, 2), kHiB = kmajor_desc_hi(1024, 2);
+      const uint64_t b_desc0 = kmajor_desc_at(kHiB, w_base);
       int stage = 0;
       uint32_t phase_bit = 0;
       int grp = 0;
@@ -152,21 +156,22 @@ conv_tc_quad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         mbar_wait(&tmem_empty[grp], grp_phase ^ 1);
         mbar_wait(&full_bar[stage], phase_bit);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + stage * kQStageBytes);
-        const uint32_t tmem_d = tmem_base + (uint32_t)(grp * kQN);
+        const uint64_t a_desc0 = kmajor_desc_at(kHiA, smem_a0 + (uint32_t)(stage * kQStageBytes));
+        const uint32_t tmem_d = tmem_u + (uint32_t)(grp * kQN);
+        if (elect_one()) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
+          for (int r = 0; r < 4; ++r) {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            // A: rows = blocks along x (128 B apart), 8-row groups = block rows (two image rows apart)
-            const uint64_t adesc = make_desc_sw128(a_base + (uint32_t)(r * kQRowPitch + 64 + kk * 32), 2 * kQRowPitch);
-            // B: K-major [128 x 64] atoms, atom = (r*128 + kk*16) / 64
-            const uint64_t bdesc = make_desc_sw128(w_base + (uint32_t)((r * 2 + (kk >> 2)) * (kQN * 128) + (kk & 3) * 32), 1024);
-            umma_bf16(tmem_d, adesc, bdesc, p.idesc, (r | kk) != 0 ? 1u : 0u);
+            for (int kk = 0; kk < 8; ++kk) {
+              // A: rows = blocks along x (128 B apart), 8-row groups = block rows (two image rows apart)
+              // B: K-major [128 x 64] atoms, atom = (r*128 + kk*16) / 64
+              umma_bf16(tmem_d, a_desc0 + (uint64_t)((r * kQRowPitch + 64 + kk * 32) >> 4),
+                        b_desc0 + (uint64_t)(((r * 2 + (kk >> 2)) * (kQN * 128) + (kk & 3) * 32) >> 4), p.idesc, (r | kk) != 0 ? 1u : 0u);
+            }
           }
+          umma_commit(&empty_bar[stage]);
+          umma_commit(&tmem_full[grp]);
         }
-        umma_commit(&empty_bar[stage]);
-        umma_commit(&tmem_full[grp]);
         if (++stage == kQStages) { stage = 0; phase_bit ^= 1; }
         if (++grp == kQGroups) { grp = 0; grp_phase ^= 1; }
       }

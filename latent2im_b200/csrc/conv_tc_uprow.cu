@@ -34,9 +34,8 @@ constexpr int kSegW = 128;                       // GEMM M: input columns per se
 constexpr int kRowPx = kSegW + 2;                // + one halo column each side
 constexpr int kPlaneBytes = kRowPx * 128;        // 16640: one 64-channel plane of one input row
 constexpr int kPlaneStride = (kPlaneBytes + 1023) & ~1023;   // 17408
-constexpr int kEpiWarps = 8;
+constexpr int kMaxEpiWarps = 16;
 constexpr int kNoiseSlots = 4;                   // ring of 1 KB noise row segments (256 output pixels, fp32)
-constexpr int kThreads = 128 + kEpiWarps * 32;
 
 // Optional cycle accounting (compile with -DL2I_UPROW_PROF, tools/probes/uprow_prof.py): lane 0 of every warp accumulates the clocks
 // it spends in each wait and dumps them to e.rgb_part (unused by this kernel) as [block][12 warps][8] counters.
@@ -44,7 +43,7 @@ constexpr int kThreads = 128 + kEpiWarps * 32;
 #define PROF_DECL long long prof_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long prof_t_ = clock64(); const long long prof_t0_ = prof_t_
 #define PROF_MARK(i) do { const long long n_ = clock64(); prof_[i] += n_ - prof_t_; prof_t_ = n_; } while (0)
 #define PROF_DUMP(p, warp) do { if ((threadIdx.x & 31) == 0 && (p).e.rgb_part != nullptr) { \
-    prof_[7] = clock64() - prof_t0_; long long* d_ = (long long*)(p).e.rgb_part + (((size_t)KC * 148 + blockIdx.x) * 12 + (warp)) * 8; \
+    prof_[7] = clock64() - prof_t0_; long long* d_ = (long long*)(p).e.rgb_part + (((size_t)KC * 148 + blockIdx.x) * 20 + (warp)) * 8; \
     for (int i_ = 0; i_ < 8; ++i_) d_[i_] = prof_[i_]; } } while (0)
 #else
 #define PROF_DECL
@@ -88,8 +87,10 @@ __device__ __forceinline__ Run decode_run(const UprowParams& p, int64_t r, int64
 
 // CO = output channels per work unit (GEMM N = 2 * CO), KC = Cin / 64, AS = input-row ring slots,
 // BRES = weights resident (all 9 * KC planes), else streamed: BP planes of one (kh, dx) tile per stage, WST stages.
-template <int CO, int KC, int AS, bool BRES, int BP, int WST>
-__global__ void __launch_bounds__(kThreads, 1)
+// EW = epilogue warps: 8 (each owns one output-pixel parity = CO accumulator columns) or, for CO = 32, 16 (16 columns each): four
+// warps per scheduler instead of two hide the barrier / tcgen05.ld / shared-memory latencies of the epilogue, which bounds the layer.
+template <int CO, int KC, int AS, bool BRES, int BP, int WST, int EW>
+__global__ void __launch_bounds__(128 + EW * 32, 1)
 conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                      const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ UprowParams p) {
   constexpr int N = 2 * CO;
@@ -97,7 +98,14 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   constexpr int kBPlaneBytes = N * 128;
   constexpr int kBBytes = BRES ? 9 * KC * kBPlaneBytes : WST * BP * kBPlaneBytes;
   constexpr int kBStageBytes = BP * kBPlaneBytes;
-  constexpr int NCHK = CO / 32;                 // 32-column chunks per epilogue warp
+  constexpr int kEpiWarps = EW;
+  constexpr int kThreads = 128 + EW * 32;
+  constexpr int CW = N / (EW / 4);              // accumulator columns per epilogue warp
+  constexpr int CK = CW < 32 ? CW : 32;         // columns per tcgen05.ld / staging tile / TMA store
+  constexpr int NCHK = CW / CK;                 // chunks per epilogue warp
+  static_assert((EW == 8 || EW == 16) && (CK == 16 || CK == 32) && CW <= CO, "epilogue warp layout");
+  // launch allocation (registers per thread) and the setmaxnreg split between the producer / MMA warpgroup and the epilogue warps
+  constexpr int kRegLaunch = EW == 8 ? 168 : 96, kRegLow = EW == 8 ? 48 : 32, kRegHigh = EW == 8 ? 224 : 112;
   constexpr int kSlots = 512 / N >= 8 ? 8 : 512 / N;   // TMEM accumulator ring (rows of Hb): 8 x 64 or 4 x 128 columns
   // Vertical FIR state per epilogue thread.  NPART = 3 (CO = 32): three running partial output rows in registers, ONE
   // tcgen05.ld per Hb row, whose slot is handed back as soon as the load has landed.  NPART = 2 (CO = 64, register budget):
@@ -110,7 +118,7 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_b = smem + AS * kASlotBytes;
-  uint8_t* smem_out = smem_b + kBBytes;          // kEpiWarps x 2 KB SWIZZLE_64B staging tiles (32 pixels x 32 channels)
+  uint8_t* smem_out = smem_b + kBBytes;          // per epilogue warp: 32 pixels x CK channels (SWIZZLE_64B rows of 64 B, or plain 32 B rows)
   __shared__ __align__(16) float epi_smem[3 * CO];
   __shared__ __align__(128) float noise_smem[kNoiseSlots][2 * kSegW];
   __shared__ __align__(8) uint64_t n_full[kNoiseSlots];
@@ -148,9 +156,9 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   // register budget: the producer / MMA warpgroup needs few, the 8 epilogue warps hold the FIR state of up to 64 channels.
   // setmaxnreg.inc can only take what .dec released inside THIS CTA's launch allocation (384 threads x 168 registers): a
   // request beyond it blocks forever (measured the hard way: 48 / 232 hangs).
-  static_assert(128 * 48 + kEpiWarps * 32 * 224 <= kThreads * 168, "setmaxnreg budget");
+  static_assert(128 * kRegLow + kEpiWarps * 32 * kRegHigh <= kThreads * kRegLaunch, "setmaxnreg budget");
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegLow));
   if (warp == 0) {
     // ===================== A producer: input rows m0-1 .. m0+R of every run =====================
     if (lane == 0) {
@@ -224,7 +232,11 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs this (warp-uniform) control flow and ONE elected lane issues each tcgen05 instruction: operands computed
+    // under `if (lane == 0)` are per-thread values to the compiler, which then moves every descriptor into uniform registers
+    // through an ELECT / R2UR.BROADCAST / BRA.U.ANY loop - ~19 instructions and > 100 clocks per MMA, more than an N = 64 MMA takes
+    // (cycle accounting, profiles/r2e_uprow_cycle_accounting.txt: the issuer spent 85-95 % of the kernel issuing).
+    {
       if (BRES) {
         mbar_wait(&w_full[0], 0);
         tc_fence_after();
@@ -233,6 +245,10 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       uint32_t abase = 0;      // ring index of the current run's first input row (m0 - 1)
       uint32_t awaited = 0;    // input rows whose "full" barrier has been observed
       uint32_t tcnt = 0, wcnt = 0;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t smem_a0 = smem_u32(smem), smem_b0 = smem_u32(smem_b);
+      // K-major SWIZZLE_128B descriptor, 8-row groups 1024 B apart: only the 14-bit start-address field (bytes >> 4) changes
+      constexpr uint64_t kDescHi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
       for (int64_t r = r_begin; r < r_end;) {
         const Run q = decode_run(p, r, r_end);
         const int nrows = 2 * q.R + 3;
@@ -244,7 +260,7 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           mbar_wait(&tmem_empty[tslot], ((tcnt / kSlots) & 1) ^ 1);
           PROF_MARK(1);                                                   // 1: waiting for a free accumulator slot
           tc_fence_after();
-          const uint32_t tmem_d = tmem_base + (uint32_t)(tslot * N);
+          const uint32_t tmem_d = tmem_u + (uint32_t)(tslot * N);
           uint32_t acc = 0;
           for (int g = 0; g < (py ? 1 : 2); ++g) {
             const int kh = py ? 1 : (g == 0 ? 2 : 0);
@@ -256,41 +272,42 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
               ++awaited;
             }
             tc_fence_after();
-            const uint32_t a_row = smem_u32(smem + (ai % AS) * kASlotBytes);
+            const uint64_t a_desc = kDescHi | (uint64_t)(((smem_a0 + (ai % AS) * kASlotBytes) >> 4) & 0x3FFF);
+#pragma unroll
             for (int dxi = 0; dxi < 3; ++dxi) {
-#pragma unroll 1
+#pragma unroll
               for (int kc = 0; kc < KC; kc += BP) {
-                uint32_t b_stage;
+                uint64_t b_desc;
                 if (BRES) {
-                  b_stage = smem_u32(smem_b + ((kh * 3 + dxi) * KC + kc) * kBPlaneBytes);
+                  b_desc = kDescHi | (uint64_t)(((smem_b0 + ((kh * 3 + dxi) * KC + kc) * kBPlaneBytes) >> 4) & 0x3FFF);
                 } else {
                   const int ws = wcnt % WST;
                   PROF_MARK(0);
                   mbar_wait(&w_full[ws], (wcnt / WST) & 1);
                   PROF_MARK(3);                                           // 3: waiting for a weight stage
                   tc_fence_after();
-                  b_stage = smem_u32(smem_b + ws * kBStageBytes);
+                  b_desc = kDescHi | (uint64_t)(((smem_b0 + ws * kBStageBytes) >> 4) & 0x3FFF);
                 }
+                if (elect_one()) {
 #pragma unroll
-                for (int j = 0; j < BP; ++j) {
-                  const uint32_t a_tap = a_row + (uint32_t)((kc + j) * kPlaneStride + dxi * 128);
-                  const uint32_t b_tile = b_stage + (uint32_t)(j * kBPlaneBytes);
+                  for (int j = 0; j < BP; ++j) {
 #pragma unroll
-                  for (int kk = 0; kk < 4; ++kk) {
-                    umma_bf16(tmem_d, uprow_desc(a_tap + kk * 32, 1024), uprow_desc(b_tile + kk * 32, 1024), kIdesc, acc);
-                    acc = 1;
+                    for (int kk = 0; kk < 4; ++kk) {
+                      // start-address field += byte offset >> 4 (all offsets are compile-time constants; no carry out of 14 bits)
+                      umma_bf16(tmem_d, a_desc + (uint64_t)(((kc + j) * kPlaneStride + dxi * 128 + kk * 32) >> 4),
+                                b_desc + (uint64_t)((j * kBPlaneBytes + kk * 32) >> 4), kIdesc, acc | (uint32_t)(j | kk));
+                    }
                   }
+                  if (!BRES) umma_commit(&w_empty[wcnt % WST]);
                 }
-                if (!BRES) {
-                  umma_commit(&w_empty[wcnt % WST]);
-                  ++wcnt;
-                }
+                acc = 1;
+                if (!BRES) ++wcnt;
               }
             }
             // input row m-1 is dead after the kh = 2 group; the run's last input row after its kh = 1 group
-            if (kh == 2 || k == nrows - 1) umma_commit(&a_empty[ai % AS]);
+            if ((kh == 2 || k == nrows - 1) && elect_one()) umma_commit(&a_empty[ai % AS]);
           }
-          umma_commit(&tmem_full[tslot]);
+          if (elect_one()) umma_commit(&tmem_full[tslot]);
         }
         abase += (uint32_t)(q.R + 2);
         r += q.R;
@@ -300,12 +317,14 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     }
   }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegHigh));
     // ===================== epilogue: vertical FIR from TMEM + noise / bias / lrelu / next-style scale =====================
     const EpiParams& e = p.e;
     const int ew = warp - 4;
     const int q4 = warp & 3;                      // TMEM lane quadrant this warp may read
-    const int hb = ew >> 2;                       // output pixel parity b: columns [hb * CO, (hb + 1) * CO)
+    const int col0 = (ew >> 2) * CW;              // this warp's first accumulator column; columns are (parity b, channel)
+    const int hb = col0 / CO;                     // output pixel parity b
+    const int cch = col0 % CO;                    // first channel (within the work unit's CO) of this warp
     const int etid = threadIdx.x - 128;
     float* s_d = epi_smem;
     float* s_b = epi_smem + CO;
@@ -314,31 +333,31 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     const bool has_noise = e.noise != nullptr;
     const float nw = (has_noise && e.noise_w != nullptr) ? __ldg(e.noise_w) * kSqrt2 : 0.f;
     const float f0 = e.fir[0], f1 = e.fir[1], f2 = e.fir[2], f3 = e.fir[3];
-    uint8_t* stage_tile = smem_out + ew * 2048;
-    __nv_bfloat16* stage_out = (__nv_bfloat16*)stage_tile + lane * 32;
-    const int stage_swz = (lane >> 1) & 3;
-    const uint32_t lane_taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(hb * CO);
+    uint8_t* stage_tile = smem_out + ew * (32 * CK * 2);
+    uint4* stage_row = reinterpret_cast<uint4*>(stage_tile + lane * (CK * 2));   // this lane's pixel: CK bf16
+    const int stage_swz = CK == 32 ? ((lane >> 1) & 3) : 0;                        // SWIZZLE_64B: 16-byte piece ^= address bits [7:8]
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)col0;
     const float* my_noise = &noise_smem[0][2 * (q4 * 32 + lane) + hb];
     PROF_DECL;
     uint32_t tcnt = 0, ncnt = 0;
-    float pa[NCHK][32], pb[NCHK][32], pc[NPART == 3 ? NCHK : 1][32];
+    float pa[NCHK][CK], pb[NCHK][CK], pc[NPART == 3 ? NCHK : 1][CK];
     for (int64_t r = r_begin; r < r_end;) {
       const Run q = decode_run(p, r, r_end);
       const int nrows = 2 * q.R + 3;
       // per-(sample, channel part) epilogue vectors
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
       for (int j = etid; j < CO; j += kEpiWarps * 32) {
         const int co = q.ch * CO + j;
         s_d[j] = (e.demod != nullptr ? __ldg(e.demod + (int64_t)q.b * e.demod_bs + co) : 1.f) * kSqrt2;
         s_b[j] = __ldg(e.bias + co) * kSqrt2;
         s_n[j] = e.s_next ? __ldg(e.s_next + (int64_t)q.b * e.s_next_bs + co) : 1.f;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
       const int xo = 2 * (q.seg * kSegW + q4 * 32) + hb;                  // first output column of this warp's 32 pixels
 #pragma unroll
       for (int c = 0; c < NCHK; ++c)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { pa[c][j] = 0.f; pb[c][j] = 0.f; if (NPART == 3) pc[c][j] = 0.f; }
+        for (int j = 0; j < CK; ++j) { pa[c][j] = 0.f; pb[c][j] = 0.f; if (NPART == 3) pc[c][j] = 0.f; }
 
       // Hb row u = 2 m0 - 1 + k.  Invariant before row k:  pa = f0 H[k-3] + f1 H[k-2] + f2 H[k-1]  (output row k-2 minus its last
       // term),  pb = f0 H[k-2] + f1 H[k-1],  pc = f0 H[k-1]  (rows before the run's first count as absent: those output rows
@@ -365,17 +384,17 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         }
 #pragma unroll
         for (int c = 0; c < NCHK; ++c) {
-          uint32_t v[32], v1[NPART == 2 ? 32 : 1];
-          tmem_ld32(t_u + c * 32, v);
+          uint32_t v[CK], v1[NPART == 2 ? CK : 1];
+          tmem_ld_n<CK>(t_u + c * CK, v);
           if (NPART == 2) {
             if (k > 0) {
-              uint32_t w1[32];
-              tmem_ld32(t_u1 + c * 32, w1);
+              uint32_t w1[CK];
+              tmem_ld_n<CK>(t_u1 + c * CK, w1);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v1[j] = w1[j];
+              for (int j = 0; j < CK; ++j) v1[j] = w1[j];
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v1[j] = 0u;
+              for (int j = 0; j < CK; ++j) v1[j] = 0u;
             }
           }
           PROF_MARK(0);
@@ -396,24 +415,42 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             }
           }
           if (fin) {
-            uint32_t o[32];
+            // y = lrelu(d * out + noise + bias) * sqrt2 (sqrt2 folded into d, bias, noise), stored as bf16 of y * s_next
+            uint32_t packed[CK / 2];
+            const float* pd = s_d + cch + c * CK;
+            const float* pbias = s_b + cch + c * CK;
+            const float* pn = s_n + cch + c * CK;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(fmaf(f3, __uint_as_float(v[j]), pa[c][j]));
-            float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+            for (int j4 = 0; j4 < CK; j4 += 4) {
+              const float4 d4 = *reinterpret_cast<const float4*>(pd + j4);
+              const float4 b4 = *reinterpret_cast<const float4*>(pbias + j4);
+              const float4 n4 = *reinterpret_cast<const float4*>(pn + j4);
+              const float dd[4] = {d4.x, d4.y, d4.z, d4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w}, nn[4] = {n4.x, n4.y, n4.z, n4.w};
+              float x[4];
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                const float o = fmaf(f3, __uint_as_float(v[j4 + h]), pa[c][j4 + h]);
+                x[h] = fmaf(o, dd[h], bb[h] + nz);
+                x[h] = fmaxf(x[h], 0.2f * x[h]) * nn[h];
+              }
+              packed[j4 >> 1] = pack_bf16(x[0], x[1]);
+              packed[(j4 >> 1) + 1] = pack_bf16(x[2], x[3]);
+            }
             PROF_MARK(0);
             if (lane == 0) tma_store_wait_read();         // the previous store has finished reading the staging tile
             __syncwarp();
             PROF_MARK(4);                                                 // 4: previous TMA store still reading the staging tile
-            epilogue_chunk32<EPI_ACT>(o, s_d + c * 32, s_b + c * 32, s_n + c * 32, nullptr, nullptr, nullptr, nz, false, r0, r1, r2,
-                                      stage_out, nullptr, stage_swz);
+#pragma unroll
+            for (int kq = 0; kq < CK / 8; ++kq)
+              stage_row[kq ^ stage_swz] = make_uint4(packed[4 * kq], packed[4 * kq + 1], packed[4 * kq + 2], packed[4 * kq + 3]);
             PROF_MARK(0);
             fence_proxy_async_smem();
             __syncwarp();
             PROF_MARK(5);                                                 // 5: proxy fence (MEMBAR) before the TMA store
-            if (lane == 0) tma_store_4d(&tmap_o, stage_tile, q.ch * CO + c * 32, xo, oy, q.b);
+            if (lane == 0) tma_store_4d(&tmap_o, stage_tile, q.ch * CO + cch + c * CK, xo, oy, q.b);
           }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int j = 0; j < CK; ++j) {
             const float x = __uint_as_float(v[j]);
             pa[c][j] = fmaf(f2, x, pb[c][j]);
             if (NPART == 3) {
@@ -440,19 +477,20 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   }
 }
 
-template <int CO, int KC, int AS, bool BRES, int BP, int WST>
+template <int CO, int KC, int AS, bool BRES, int BP, int WST, int EW>
 int launch_uprow_variant(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const UprowParams& p, cudaStream_t st) {
   constexpr int N = 2 * CO;
-  constexpr int smem = AS * KC * kPlaneStride + (BRES ? 9 * KC : WST * BP) * N * 128 + kEpiWarps * 2048 + 1024;
+  constexpr int CK = (N / (EW / 4)) < 32 ? (N / (EW / 4)) : 32;
+  constexpr int smem = AS * KC * kPlaneStride + (BRES ? 9 * KC : WST * BP) * N * 128 + EW * 32 * CK * 2 + 1024;
   static_assert(smem + 3 * CO * 4 + kNoiseSlots * 1024 + 512 <= 227 * 1024, "shared memory budget (dynamic + static)");
-  auto kern = conv_tc_uprow_kernel<CO, KC, AS, BRES, BP, WST>;
+  auto kern = conv_tc_uprow_kernel<CO, KC, AS, BRES, BP, WST, EW>;
   static bool attr_set = false;
   if (!attr_set) {
     L2I_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   const int grid = (int)std::min<int64_t>(p.total_rows, kNumSMs);
-  kern<<<grid, kThreads, smem, st>>>(ta, tw, to, p);
+  kern<<<grid, 128 + EW * 32, smem, st>>>(ta, tw, to, p);
   return check_launch("conv_tc_uprow");
 }
 
@@ -530,14 +568,16 @@ int launch_conv_tc_uprow(const void* in, const __nv_bfloat16* w, const ConvGeom&
     // output NHWC [B][2H][2W][Cout] bf16; an epilogue warp stores 32 channels of every other pixel of 64 consecutive pixels
     const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)(2 * g.W), (uint64_t)(2 * g.H), (uint64_t)g.B};
     const uint64_t str[4] = {2, (uint64_t)Cout * 2, (uint64_t)2 * g.W * Cout * 2, (uint64_t)4 * g.H * g.W * Cout * 2};
-    const uint32_t box[4] = {32, 64, 1, 1};
+    // (the 16-warp variant stores 16 channels = 32-byte rows, no swizzle)
+    const uint32_t ck = CO == 32 ? 16 : 32;
+    const uint32_t box[4] = {ck, 64, 1, 1};
     const uint32_t estr[4] = {1, 2, 1, 1};
-    L2I_TRY(make_tmap_strided(&to, e.out, 4, dims, str, box, estr, CU_TENSOR_MAP_SWIZZLE_64B));
+    L2I_TRY(make_tmap_strided(&to, e.out, 4, dims, str, box, estr, ck == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE));
   }
-  if (CO == 32) return launch_uprow_variant<32, 1, 4, true, 1, 1>(ta, tw, to, p, st);
-  if (g.Cin == 128) return launch_uprow_variant<64, 2, 2, false, 2, 4>(ta, tw, to, p, st);
+  if (CO == 32) return launch_uprow_variant<32, 1, 4, true, 1, 1, 16>(ta, tw, to, p, st);
+  if (g.Cin == 128) return launch_uprow_variant<64, 2, 2, false, 2, 4, 8>(ta, tw, to, p, st);
   // Cin = 256: two input rows are 136 KB, which leaves a 4 x 16 KB weight ring (one 64-channel plane per stage)
-  return launch_uprow_variant<64, 4, 2, false, 1, 4>(ta, tw, to, p, st);
+  return launch_uprow_variant<64, 4, 2, false, 1, 4, 8>(ta, tw, to, p, st);
 }
 
 }  // namespace l2i

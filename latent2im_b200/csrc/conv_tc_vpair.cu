@@ -149,38 +149,43 @@ conv_tc_vpair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     }
   } else if (warp == 1) {
     // ===================== MMA issuer: 48 MMAs per tile, no barrier inside a tile =====================
-    if (lane == 0) {
+    // warp-uniform control flow, one elected lane issues (tc_ptx.cuh: elect_one)
+    {
       mbar_wait(&w_bar, 0);
       tc_fence_after();
-      const uint32_t w_base = smem_u32(smem_w);
+      const uint32_t w_base = smem_u32(smem_w), smem_a0 = smem_u32(smem);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      constexpr uint64_t kHiA = kmajor_desc_hi(2 * kVW * 128, 2), kHiB = kmajor_desc_hi(1024, 2);
+      const uint64_t b_desc0 = kmajor_desc_at(kHiB, w_base);
       int stage = 0, acc = 0;
       uint32_t phase_bit = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         mbar_wait(&full_bar[stage], phase_bit);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + stage * kVStageBytes);
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * N);
-        // input-row order 1, 2, 0, 3: the first MMA (r = 1, N = 128) initialises all 128 accumulator columns
+        const uint64_t a_desc0 = kmajor_desc_at(kHiA, smem_a0 + (uint32_t)(stage * kVStageBytes));
+        const uint32_t tmem_d = tmem_u + (uint32_t)(acc * N);
+        if (elect_one()) {
+          // input-row order 1, 2, 0, 3: the first MMA (r = 1, N = 128) initialises all 128 accumulator columns
 #pragma unroll
-        for (int ri = 0; ri < 4; ++ri) {
-          const int r = ri == 0 ? 1 : (ri == 1 ? 2 : (ri == 2 ? 0 : 3));
-          // weight window: slots per kw are W[kh=2], W[kh=1], W[kh=0]; parity 0 uses kh = r, parity 1 kh = r - 1
-          const int slot = r == 0 ? 2 : (r == 1 ? 1 : 0);            // first 64-row slot of the operand
-          const bool wide = (r == 1 || r == 2);                      // N = 128 (both parities) or N = 64
-          const uint32_t d_col = r == 3 ? 64u : 0u;                  // r = 3 feeds parity 1 only
+          for (int ri = 0; ri < 4; ++ri) {
+            const int r = ri == 0 ? 1 : (ri == 1 ? 2 : (ri == 2 ? 0 : 3));
+            // weight window: slots per kw are W[kh=2], W[kh=1], W[kh=0]; parity 0 uses kh = r, parity 1 kh = r - 1
+            const int slot = r == 0 ? 2 : (r == 1 ? 1 : 0);            // first 64-row slot of the operand
+            const bool wide = (r == 1 || r == 2);                      // N = 128 (both parities) or N = 64
+            const uint32_t d_col = r == 3 ? 64u : 0u;                  // r = 3 feeds parity 1 only
 #pragma unroll
-          for (int kw = 0; kw < 3; ++kw) {
-            const uint32_t a_tap = a_base + (uint32_t)((r * kVW + kw) * 128);
-            const uint32_t b_tap = w_base + (uint32_t)((kw * 3 + slot) * (64 * 128));
+            for (int kw = 0; kw < 3; ++kw) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_d + d_col, vp_desc(a_tap + k * 32, 2 * kVW * 128), vp_desc(b_tap + k * 32, 1024),
-                        wide ? p.idesc128 : p.idesc64, (ri | kw | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem_d + d_col, a_desc0 + (uint64_t)(((r * kVW + kw) * 128 + k * 32) >> 4),
+                          b_desc0 + (uint64_t)(((kw * 3 + slot) * (64 * 128) + k * 32) >> 4), wide ? p.idesc128 : p.idesc64,
+                          (ri | kw | k) != 0 ? 1u : 0u);
+            }
           }
+          umma_commit(&empty_bar[stage]);
+          umma_commit(&tmem_full[acc]);
         }
-        umma_commit(&empty_bar[stage]);
-        umma_commit(&tmem_full[acc]);
         if (++stage == kVStages) { stage = 0; phase_bit ^= 1; }
         if (++acc == kVAccs) { acc = 0; acc_phase ^= 1; }
       }

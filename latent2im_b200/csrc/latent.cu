@@ -1,6 +1,8 @@
 // Latent-side kernels: fused linear (mapping network / walk MLPs), PixelNorm, and the walk steps.
 // These are launch- and latency-bound (B <= a few hundred rows of 512 floats); each output element
 // is one warp-level dot product, weights stream once from L2, inputs sit in shared memory.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace l2i {
@@ -127,7 +129,8 @@ int launch_linear(float* y, int64_t y_stride, const float* x, int64_t x_stride, 
   const size_t bt_smem = (size_t)K * 32 * sizeof(float);
   // taken for EVERY batch size (not only the large ones): the summation order must not depend on the batch, image i of a
   // batch is bit-identical to the same latent run alone (tests/test_gpu_generator.py::test_large_batch_matches_single_sample_runs)
-  if (K % 4 == 0 && bt_smem <= 96 * 1024 && ((uintptr_t)W % 16 == 0)) {
+  static const bool bt_off = std::getenv("L2I_LINEAR_BT") != nullptr && std::atoi(std::getenv("L2I_LINEAR_BT")) == 0;   // debug A/B
+  if (!bt_off && K % 4 == 0 && bt_smem <= 96 * 1024 && ((uintptr_t)W % 16 == 0)) {
     static bool attr_set = false;
     if (!attr_set) {
       L2I_CUDA_TRY(cudaFuncSetAttribute(linear_bt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));

@@ -92,6 +92,17 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+template <int NCOL> __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&v)[NCOL]);
+template <> __device__ __forceinline__ void tmem_ld_n<32>(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld32(taddr, v); }
+template <> __device__ __forceinline__ void tmem_ld_n<16>(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld16(taddr, v); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp): rows are
@@ -105,6 +116,22 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_
   d |= (uint64_t)(layout_type & 7) << 61;                  // layout type [61,64): 2 = SW128, 4 = SW64
   return d;
 }
+
+// One lane of a converged warp (elect.sync).  MMA-issuing warps run their (warp-uniform) control flow on all 32 lanes and wrap
+// only the tcgen05 instructions in `if (elect_one())`: operands computed under `if (lane == 0)` are per-thread values to the
+// compiler, which then moves every descriptor into uniform registers through an ELECT / R2UR.BROADCAST / BRA.U.ANY loop, ~19
+// instructions and > 100 clocks per MMA - more than an N <= 128 MMA takes (measured, profiles/r2e_uprow_cycle_accounting_before.txt).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// Constant upper part of a K-major descriptor; the full descriptor is  desc_hi | ((smem_addr >> 4) & 0x3FFF)  and offsets that do
+// not carry out of the 14-bit start-address field can simply be added: desc + (byte_offset >> 4).
+__host__ __device__ constexpr uint64_t kmajor_desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+  return ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)(layout_type & 7) << 61);
+}
+__device__ __forceinline__ uint64_t kmajor_desc_at(uint64_t hi, uint32_t smem_addr) { return hi | (uint64_t)((smem_addr >> 4) & 0x3FFF); }
 
 // cute::UMMA::InstrDescriptor for kind::f16: c=F32 (1<<4), a=b=BF16 (1<<7, 1<<10), K-major A and B,
 // n_dim = N>>3 at bit 17, m_dim = M>>4 at bit 24.

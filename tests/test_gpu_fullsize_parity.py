@@ -77,8 +77,11 @@ def test_fp32_path_matches_reference_fixture(tag):
     max_abs, _ = _image_errors(tag, img, z)
     assert max_abs <= 1e-3, f"{tag}: fp32 max-abs {max_abs:.3e} (image spans {span:.1f})"
     gref = torch.from_numpy(z[f"{tag}_grad_latent"])
+    # leaky-relu kinks make single gradient components differ by ~1e-3 of the maximum between two fp32 implementations
+    # (an activation within rounding of 0 takes the other slope): gate the relative L2 error, bound the max norm loosely
     gerr = (glat.cpu() - gref).abs().max().item() / gref.abs().max().item()
-    assert gerr <= 2e-3, f"{tag}: fp32 latent gradient relative max error {gerr:.3e}"
+    gl2 = ((glat.cpu().double() - gref.double()).norm() / gref.double().norm()).item()
+    assert gl2 <= 4e-3 and gerr <= 2e-2, f"{tag}: fp32 latent gradient relative L2 error {gl2:.3e}, max {gerr:.3e}"
 
 
 @pytest.mark.parametrize("tag,gate_p2p2", [("s256", 45.0), ("s1024", 40.0)])

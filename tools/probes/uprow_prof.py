@@ -28,13 +28,13 @@ def main():
             gen(lat, input_is_latent=True)
     torch.cuda.synchronize()
     h = gen._handle(dev, b)
-    n = 5 * 148 * 12 * 8
+    n = 5 * 148 * 20 * 8
     buf = np.zeros(n, dtype=np.int64)
     fn = h.lib.l2i_debug_read_rgb_part
     fn.restype = C.c_int
     fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     assert fn(h.handle, buf.ctypes.data, buf.nbytes) == 0
-    buf = buf.reshape(5, 148, 12, 8)
+    buf = buf.reshape(5, 148, 20, 8)
     names_mma = ["issue", "wait tmem_empty", "wait a_full", "wait w_full", "-", "-", "-", "total"]
     names_epi = ["work", "wait tmem_full", "wait noise", "tcgen05.ld", "wait prev TMA store", "proxy fence", "-", "total"]
     for kc, layer in ((4, "convs.10 256->128"), (2, "convs.12 128->64"), (1, "convs.14 64->32")):
@@ -44,7 +44,7 @@ def main():
         print(f"--- KC={kc} ({layer}) ---")
         tot = blk[:, 1, 7].mean()
         print(f"  MMA issuer: total {tot:.0f} clk/CTA; " + ", ".join(f"{nm} {100 * blk[:, 1, i].mean() / tot:.1f}%" for i, nm in enumerate(names_mma[:4])))
-        for w in range(4, 12):
+        for w in range(4, 4 + (16 if kc == 1 else 8)):
             tot = blk[:, w, 7].mean()
             print(f"  epilogue warp {w} (quadrant {w & 3}, parity {(w - 4) >> 2}): total {tot:.0f}; " +
                   ", ".join(f"{nm} {100 * blk[:, w, i].mean() / tot:.1f}%" for i, nm in enumerate(names_epi[:6])))
