@@ -461,6 +461,8 @@ def _resnet50_regressor(dev, amp):
     reg = torchvision.models.resnet50(weights=None)
     reg.fc = torch.nn.Linear(2048, 40)
     reg = torch.nn.Sequential(reg, torch.nn.Sigmoid()).to(dev).eval()
+    from latent2im_b200.regressor import fold_batchnorm
+    reg = fold_batchnorm(reg, inplace=True)       # frozen eval-mode BN folded into the convs (as TransformGraph.get_reg_module does)
     if amp:
         reg = reg.to(memory_format=torch.channels_last)
     for p_ in reg.parameters():

@@ -31,6 +31,7 @@ void refresh_kernel_switches() {
   s.vpair = flag("L2I_VPAIR", 1) != 0;
   s.fir_simt = flag("L2I_FIR_SIMT", 0) != 0;
   s.uprow = flag("L2I_UPROW", 1) != 0;
+  s.uprow_mask = flag("L2I_UPROW_MASK", 7);
   g_switches = s;
 }
 

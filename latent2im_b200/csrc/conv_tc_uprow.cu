@@ -104,6 +104,10 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   constexpr int CK = CW < 32 ? CW : 32;         // columns per tcgen05.ld / staging tile / TMA store
   constexpr int NCHK = CW / CK;                 // chunks per epilogue warp
   static_assert((EW == 8 || EW == 16) && (CK == 16 || CK == 32) && CW <= CO, "epilogue warp layout");
+  // DIRECT (16-column warps): a lane's 16 bf16 channels are one full 32-byte sector of the NHWC output, so they leave as two
+  // 16-byte global stores - no staging tile, no proxy fence (a MEMBAR that waits for every outstanding load of the thread), no
+  // TMA-store bookkeeping - and the noise value is a plain global load issued one row ahead instead of the shared-memory ring.
+  constexpr bool DIRECT = CK == 16;
   // launch allocation (registers per thread) and the setmaxnreg split between the producer / MMA warpgroup and the epilogue warps
   constexpr int kRegLaunch = EW == 8 ? 168 : 96, kRegLow = EW == 8 ? 48 : 32, kRegHigh = EW == 8 ? 224 : 112;
   constexpr int kSlots = 512 / N >= 8 ? 8 : 512 / N;   // TMEM accumulator ring (rows of Hb): 8 x 64 or 4 x 128 columns
@@ -173,7 +177,7 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         const Run q = decode_run(p, r, r_end);
         for (int row = q.m0 - 1; row <= q.m0 + q.R; ++row, ++acnt) {
           const int slot = acnt % AS;
-          mbar_wait(&a_empty[slot], ((acnt / AS) & 1) ^ 1);
+          mbar_wait_sleep(&a_empty[slot], ((acnt / AS) & 1) ^ 1);
           mbar_expect_tx(&a_full[slot], KC * kPlaneBytes);
 #pragma unroll
           for (int kc = 0; kc < KC; ++kc)
@@ -197,7 +201,7 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 #pragma unroll 1
               for (int kc = 0; kc < KC; kc += BP, ++wcnt) {
                 const int ws = wcnt % WST;
-                mbar_wait(&w_empty[ws], ((wcnt / WST) & 1) ^ 1);
+                mbar_wait_sleep(&w_empty[ws], ((wcnt / WST) & 1) ^ 1);
                 mbar_expect_tx(&w_full[ws], kBStageBytes);
 #pragma unroll
                 for (int j = 0; j < BP; ++j)
@@ -213,14 +217,14 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   } else if (warp == 2) {
     // ===================== noise producer: the 256-pixel fp32 noise segment of every output row, a few rows ahead ==========
     // (a global load in the epilogue threads would be waited for by the MEMBAR of every fence.proxy.async before a TMA store)
-    if (lane == 0 && p.e.noise != nullptr) {
+    if (!DIRECT && lane == 0 && p.e.noise != nullptr) {
       uint32_t ncnt = 0;
       for (int64_t r = r_begin; r < r_end;) {
         const Run q = decode_run(p, r, r_end);
         const float* src = p.e.noise + (int64_t)q.b * p.e.noise_bs + (int64_t)(2 * q.m0) * (2 * p.W) + 2 * q.seg * kSegW;
         for (int j = 0; j < 2 * q.R; ++j, ++ncnt) {
           const int slot = ncnt % kNoiseSlots;
-          mbar_wait(&n_empty[slot], ((ncnt / kNoiseSlots) & 1) ^ 1);
+          mbar_wait_sleep(&n_empty[slot], ((ncnt / kNoiseSlots) & 1) ^ 1);
           mbar_expect_tx(&n_full[slot], 2 * kSegW * 4);
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                            smem_u32(&noise_smem[slot][0])),
@@ -232,10 +236,11 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // The whole warp runs this (warp-uniform) control flow and ONE elected lane issues each tcgen05 instruction: operands computed
-    // under `if (lane == 0)` are per-thread values to the compiler, which then moves every descriptor into uniform registers
-    // through an ELECT / R2UR.BROADCAST / BRA.U.ANY loop - ~19 instructions and > 100 clocks per MMA, more than an N = 64 MMA takes
-    // (cycle accounting, profiles/r2e_uprow_cycle_accounting.txt: the issuer spent 85-95 % of the kernel issuing).
+    // The whole warp runs this (warp-uniform) control flow and ONE elected lane issues the tcgen05 instructions (tc_ptx.cuh:
+    // elect_one).  The issuing warp shares its scheduler with busy epilogue warps and is a single dependent instruction stream,
+    // so its instruction count per Hb row bounds the kernel (cycle accounting: 85-95 % of the kernel "issuing" at ~110 clocks per
+    // MMA even with uniform-register descriptors): each row is therefore ONE elected block of fully unrolled MMAs whose
+    // descriptors are the row's base descriptor plus compile-time constants, with the barrier commits inside the same block.
     {
       if (BRES) {
         mbar_wait(&w_full[0], 0);
@@ -248,66 +253,98 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t smem_a0 = smem_u32(smem), smem_b0 = smem_u32(smem_b);
       // K-major SWIZZLE_128B descriptor, 8-row groups 1024 B apart: only the 14-bit start-address field (bytes >> 4) changes
-      constexpr uint64_t kDescHi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+      constexpr uint64_t kDescHi = kmajor_desc_hi(1024, 2);
+      const uint64_t b_desc0 = kmajor_desc_at(kDescHi, smem_b0);
+      // the 3 dx x KC x 4 MMAs of one (kh, input row) group; resident weights: tile (kh, dx), plane kc at a constant offset
+      auto issue_resident = [&](int kh, uint64_t a_desc, uint32_t tmem_d, uint32_t first) {
+#pragma unroll
+        for (int dxi = 0; dxi < 3; ++dxi)
+#pragma unroll
+          for (int kc = 0; kc < KC; ++kc)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16(tmem_d, a_desc + (uint64_t)((kc * kPlaneStride + dxi * 128 + kk * 32) >> 4),
+                        b_desc0 + (uint64_t)((((kh * 3 + dxi) * KC + kc) * kBPlaneBytes + kk * 32) >> 4), kIdesc,
+                        (first == 0 && dxi == 0 && kc == 0 && kk == 0) ? 0u : 1u);
+      };
+      // streamed weights: one ring stage (BP planes of tile (kh, dx)) per elected block
+      auto issue_streamed = [&](uint64_t a_desc, uint32_t tmem_d, uint32_t first) {
+#pragma unroll
+        for (int dxi = 0; dxi < 3; ++dxi) {
+#pragma unroll
+          for (int kc = 0; kc < KC; kc += BP) {
+            const int ws = wcnt % WST;
+            PROF_MARK(0);
+            mbar_wait(&w_full[ws], (wcnt / WST) & 1);
+            PROF_MARK(3);                                           // 3: waiting for a weight stage
+            tc_fence_after();
+            const uint64_t b_desc = kmajor_desc_at(kDescHi, smem_b0 + (uint32_t)(ws * kBStageBytes));
+            if (elect_one()) {
+#pragma unroll
+              for (int j = 0; j < BP; ++j)
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_bf16(tmem_d, a_desc + (uint64_t)(((kc + j) * kPlaneStride + dxi * 128 + kk * 32) >> 4),
+                            b_desc + (uint64_t)((j * kBPlaneBytes + kk * 32) >> 4), kIdesc,
+                            (first == 0 && dxi == 0 && kc == 0 && j == 0 && kk == 0) ? 0u : 1u);
+              umma_commit(&w_empty[ws]);
+            }
+            ++wcnt;
+          }
+        }
+      };
       for (int64_t r = r_begin; r < r_end;) {
         const Run q = decode_run(p, r, r_end);
         const int nrows = 2 * q.R + 3;
         for (int k = 0; k < nrows; ++k, ++tcnt) {
-          const int py = (k & 1) ^ 1;
           const int ml = (k + 1) >> 1;                      // ring-local index of input row m = floor(u / 2): m - (m0 - 1)
           const int tslot = tcnt % kSlots;
           PROF_MARK(0);                                                   // 0: issue / loop overhead
           mbar_wait(&tmem_empty[tslot], ((tcnt / kSlots) & 1) ^ 1);
           PROF_MARK(1);                                                   // 1: waiting for a free accumulator slot
-          tc_fence_after();
           const uint32_t tmem_d = tmem_u + (uint32_t)(tslot * N);
-          uint32_t acc = 0;
-          for (int g = 0; g < (py ? 1 : 2); ++g) {
-            const int kh = py ? 1 : (g == 0 ? 2 : 0);
-            const uint32_t ai = abase + (uint32_t)(kh == 2 ? ml - 1 : ml);
-            while (awaited <= ai) {
-              PROF_MARK(0);
-              mbar_wait(&a_full[awaited % AS], (awaited / AS) & 1);
-              PROF_MARK(2);                                               // 2: waiting for an input row
-              ++awaited;
+          const uint32_t ai = abase + (uint32_t)ml;          // input row m (kh 0 / kh 1); kh 2 reads row m - 1 = ai - 1
+          while (awaited <= ai) {
+            PROF_MARK(0);
+            mbar_wait(&a_full[awaited % AS], (awaited / AS) & 1);
+            PROF_MARK(2);                                                 // 2: waiting for an input row
+            ++awaited;
+          }
+          tc_fence_after();
+          const uint64_t a_m = kmajor_desc_at(kDescHi, smem_a0 + (ai % AS) * kASlotBytes);
+          if (k & 1) {
+            // u even (py = 0): kh = 2 on row m - 1, which is dead afterwards, then kh = 0 on row m
+            const uint64_t a_m1 = kmajor_desc_at(kDescHi, smem_a0 + ((ai - 1) % AS) * kASlotBytes);
+            if (BRES) {
+              if (elect_one()) {
+                issue_resident(2, a_m1, tmem_d, 0);
+                umma_commit(&a_empty[(ai - 1) % AS]);
+                issue_resident(0, a_m, tmem_d, 1);
+                umma_commit(&tmem_full[tslot]);
+              }
+            } else {
+              issue_streamed(a_m1, tmem_d, 0);
+              if (elect_one()) umma_commit(&a_empty[(ai - 1) % AS]);
+              issue_streamed(a_m, tmem_d, 1);
+              if (elect_one()) umma_commit(&tmem_full[tslot]);
             }
-            tc_fence_after();
-            const uint64_t a_desc = kDescHi | (uint64_t)(((smem_a0 + (ai % AS) * kASlotBytes) >> 4) & 0x3FFF);
-#pragma unroll
-            for (int dxi = 0; dxi < 3; ++dxi) {
-#pragma unroll
-              for (int kc = 0; kc < KC; kc += BP) {
-                uint64_t b_desc;
-                if (BRES) {
-                  b_desc = kDescHi | (uint64_t)(((smem_b0 + ((kh * 3 + dxi) * KC + kc) * kBPlaneBytes) >> 4) & 0x3FFF);
-                } else {
-                  const int ws = wcnt % WST;
-                  PROF_MARK(0);
-                  mbar_wait(&w_full[ws], (wcnt / WST) & 1);
-                  PROF_MARK(3);                                           // 3: waiting for a weight stage
-                  tc_fence_after();
-                  b_desc = kDescHi | (uint64_t)(((smem_b0 + ws * kBStageBytes) >> 4) & 0x3FFF);
-                }
-                if (elect_one()) {
-#pragma unroll
-                  for (int j = 0; j < BP; ++j) {
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                      // start-address field += byte offset >> 4 (all offsets are compile-time constants; no carry out of 14 bits)
-                      umma_bf16(tmem_d, a_desc + (uint64_t)(((kc + j) * kPlaneStride + dxi * 128 + kk * 32) >> 4),
-                                b_desc + (uint64_t)((j * kBPlaneBytes + kk * 32) >> 4), kIdesc, acc | (uint32_t)(j | kk));
-                    }
-                  }
-                  if (!BRES) umma_commit(&w_empty[wcnt % WST]);
-                }
-                acc = 1;
-                if (!BRES) ++wcnt;
+          } else {
+            // u odd (py = 1): kh = 1 on row m; the run's last input row is dead after its kh = 1 group
+            const bool last = k == nrows - 1;
+            if (BRES) {
+              if (elect_one()) {
+                issue_resident(1, a_m, tmem_d, 0);
+                if (last) umma_commit(&a_empty[ai % AS]);
+                umma_commit(&tmem_full[tslot]);
+              }
+            } else {
+              issue_streamed(a_m, tmem_d, 0);
+              if (elect_one()) {
+                if (last) umma_commit(&a_empty[ai % AS]);
+                umma_commit(&tmem_full[tslot]);
               }
             }
-            // input row m-1 is dead after the kh = 2 group; the run's last input row after its kh = 1 group
-            if ((kh == 2 || k == nrows - 1) && elect_one()) umma_commit(&a_empty[ai % AS]);
           }
-          if (elect_one()) umma_commit(&tmem_full[tslot]);
         }
         abase += (uint32_t)(q.R + 2);
         r += q.R;
@@ -354,6 +391,12 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
       const int xo = 2 * (q.seg * kSegW + q4 * 32) + hb;                  // first output column of this warp's 32 pixels
+      const int out_W = 2 * p.W;
+      // DIRECT: this lane's pixel column in output row 0 of the sample, and its noise column
+      __nv_bfloat16* opix = (__nv_bfloat16*)e.out + (((int64_t)q.b * (2 * p.H)) * out_W + xo + 2 * lane) * p.Cout + q.ch * CO + cch;
+      const float* nptr = has_noise ? e.noise + (int64_t)q.b * e.noise_bs + xo + 2 * lane : nullptr;
+      float nz_raw = 0.f;
+      if (DIRECT && has_noise) nz_raw = __ldg(nptr + (int64_t)(2 * q.m0) * out_W);
 #pragma unroll
       for (int c = 0; c < NCHK; ++c)
 #pragma unroll
@@ -365,19 +408,28 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       for (int k = 0; k < nrows; ++k, ++tcnt) {
         const int oy = 2 * q.m0 + k - 3;                                  // output row finished by Hb row k
         const bool fin = k >= 3;
+        float nz = 0.f;
+        if (DIRECT) {
+          nz = nw * nz_raw;                                               // loaded one row ago
+          if (has_noise && k >= 2 && k + 1 < nrows) nz_raw = __ldg(nptr + (int64_t)(oy + 1) * out_W);
+        }
         PROF_MARK(0);                                                     // 0: arithmetic, staging stores, TMA store issue
         mbar_wait(&tmem_full[tcnt % kSlots], (tcnt / kSlots) & 1);
         PROF_MARK(1);                                                     // 1: waiting for the Hb row (MMA)
         tc_fence_after();
         const uint32_t t_u = lane_taddr + (uint32_t)((tcnt % kSlots) * N);
         const uint32_t t_u1 = lane_taddr + (uint32_t)(((tcnt + kSlots - 1) % kSlots) * N);
-        float nz = 0.f;
-        if (fin && has_noise) {                                           // this row's noise segment (bulk-copied by warp 2)
+        if (!DIRECT && fin && has_noise) {                                // this row's noise segment (bulk-copied by warp 2)
           const int slot = ncnt % kNoiseSlots;
           PROF_MARK(0);
           mbar_wait(&n_full[slot], (ncnt / kNoiseSlots) & 1);
           PROF_MARK(2);                                                   // 2: waiting for the noise row
           nz = nw * my_noise[slot * 2 * kSegW];
+          // hand the slot back only after the load has been PERFORMED: an mbarrier.arrive orders nothing but the issue of the earlier
+          // LDS (ptxas even schedules the arrive ahead of the load's first use), and the producer refills the slot at once (DESIGN
+          // section 10; this raced once the producers' timing changed: the noise of row + 4 in a handful of pixels, caught by the
+          // batch-invariance test)
+          __threadfence_block();                                          // MEMBAR: the LDS above has been performed
           __syncwarp();
           if (lane == 0) mbar_arrive(&n_empty[slot]);
           ++ncnt;
@@ -436,18 +488,24 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
               packed[j4 >> 1] = pack_bf16(x[0], x[1]);
               packed[(j4 >> 1) + 1] = pack_bf16(x[2], x[3]);
             }
-            PROF_MARK(0);
-            if (lane == 0) tma_store_wait_read();         // the previous store has finished reading the staging tile
-            __syncwarp();
-            PROF_MARK(4);                                                 // 4: previous TMA store still reading the staging tile
+            if (DIRECT) {
+              uint4* dst = reinterpret_cast<uint4*>(opix + (int64_t)oy * out_W * p.Cout + c * CK);
 #pragma unroll
-            for (int kq = 0; kq < CK / 8; ++kq)
-              stage_row[kq ^ stage_swz] = make_uint4(packed[4 * kq], packed[4 * kq + 1], packed[4 * kq + 2], packed[4 * kq + 3]);
-            PROF_MARK(0);
-            fence_proxy_async_smem();
-            __syncwarp();
-            PROF_MARK(5);                                                 // 5: proxy fence (MEMBAR) before the TMA store
-            if (lane == 0) tma_store_4d(&tmap_o, stage_tile, q.ch * CO + cch + c * CK, xo, oy, q.b);
+              for (int kq = 0; kq < CK / 8; ++kq) dst[kq] = make_uint4(packed[4 * kq], packed[4 * kq + 1], packed[4 * kq + 2], packed[4 * kq + 3]);
+            } else {
+              PROF_MARK(0);
+              if (lane == 0) tma_store_wait_read();         // the previous store has finished reading the staging tile
+              __syncwarp();
+              PROF_MARK(4);                                               // 4: previous TMA store still reading the staging tile
+#pragma unroll
+              for (int kq = 0; kq < CK / 8; ++kq)
+                stage_row[kq ^ stage_swz] = make_uint4(packed[4 * kq], packed[4 * kq + 1], packed[4 * kq + 2], packed[4 * kq + 3]);
+              PROF_MARK(0);
+              fence_proxy_async_smem();
+              __syncwarp();
+              PROF_MARK(5);                                               // 5: proxy fence (MEMBAR) before the TMA store
+              if (lane == 0) tma_store_4d(&tmap_o, stage_tile, q.ch * CO + cch + c * CK, xo, oy, q.b);
+            }
           }
 #pragma unroll
           for (int j = 0; j < CK; ++j) {
@@ -531,6 +589,7 @@ int uprow_co(int Cin, int Cout) {
 bool conv_tc_uprow_supported(const ConvGeom& g, const EpiParams& e) {
   if (!g_switches.uprow || !tmap_available()) return false;
   if (g.up_cout <= 0 || uprow_co(g.Cin, g.up_cout) == 0) return false;
+  if (!(g_switches.uprow_mask & (g.Cin == 64 ? 1 : (g.Cin == 128 ? 2 : 4)))) return false;
   if (g.W % kSegW != 0 || g.H < 2 || g.out_pair_packed || e.mode != 0 || e.wr != nullptr || e.y_out != nullptr) return false;
   return e.out != nullptr && (uintptr_t)e.out % 16 == 0;
 }

@@ -55,11 +55,13 @@ linear_kernel(float* __restrict__ y, int64_t y_stride, const float* __restrict__
 // + 4 LDS + 16 FMA, no cross-lane reduction, one 16-byte store per lane.  Weights are read once per 32 batch rows.
 // Requires the rows of one 4-row group to share row_xoff (true for the generator: every Cin is a multiple of 4).
 constexpr int kLinBtWarps = 8;
+constexpr int kXsPitch = 33;
 __global__ void __launch_bounds__(kLinBtWarps * 32)
 linear_bt_kernel(float* __restrict__ y, int64_t y_stride, const float* __restrict__ x, int64_t x_stride,
                  const int* __restrict__ row_xoff, const float* __restrict__ W, const float* __restrict__ bias,
                  int B, int N, int K, float wscale, float bscale, int act, float alpha, float gain, int groups_per_block) {
-  extern __shared__ float xs[];   // [K][32]
+  extern __shared__ float xs[];   // [K][33] input tile (transposed, padded), then [kLinBtWarps][4][K] weight slabs (16-byte aligned)
+  float* ws_all = xs + ((K * kXsPitch + 3) & ~3);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b0 = blockIdx.y * 32;
   const int g_begin = blockIdx.x * groups_per_block, g_end = min(g_begin + groups_per_block, (N + 3) / 4);
@@ -71,9 +73,25 @@ linear_bt_kernel(float* __restrict__ y, int64_t y_stride, const float* __restric
     const int xoff_last = row_xoff != nullptr ? row_xoff[min((min(gb + kLinBtWarps, g_end)) * 4 - 1, N - 1)] : 0;
     if (xoff_blk != staged_xoff) {
       __syncthreads();
-      for (int i = threadIdx.x; i < K * 32; i += blockDim.x) {
-        const int bb = i / K, k = i - bb * K;          // coalesced read of row bb, transposed write
-        xs[k * 32 + bb] = (b0 + bb < B) ? x[(int64_t)(b0 + bb) * x_stride + xoff_blk + k] : 0.f;
+      // x tile: one burst of 16-byte cp.async copies (row-major, rows >= B zero-filled) into the weight-slab region, then a
+      // shared -> shared transpose into the padded [K][33] layout (a register-staged loop costs one L2 round trip per element:
+      // 28 us per tile, measured)
+      {
+        const int kq = K >> 2;                                       // 16-byte chunks per row
+        for (int c = threadIdx.x; c < 32 * kq; c += blockDim.x) {
+          const int bb = c / kq, q4 = c - bb * kq;
+          const bool ok = b0 + bb < B;
+          const float* src = x + (int64_t)(ok ? b0 + bb : 0) * x_stride + xoff_blk + 4 * q4;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(ws_all + bb * K + 4 * q4)),
+                       "l"(src), "r"(ok ? 16 : 0)
+                       : "memory");
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();
+        for (int i = threadIdx.x; i < K * 32; i += blockDim.x) {
+          const int bb = i / K, k = i - bb * K;
+          xs[k * kXsPitch + bb] = ws_all[i];
+        }
       }
       __syncthreads();
       staged_xoff = xoff_blk;
@@ -88,18 +106,30 @@ linear_bt_kernel(float* __restrict__ y, int64_t y_stride, const float* __restric
         const float* w1 = W + (int64_t)min(n0 + 1, N - 1) * K;
         const float* w2 = W + (int64_t)min(n0 + 2, N - 1) * K;
         const float* w3 = W + (int64_t)min(n0 + 3, N - 1) * K;
+        // The four weight rows (4 x K floats) are fetched with ONE burst of cp.async copies into this warp's shared-memory
+        // slab and read back as broadcast LDS.128: a register-fed loop keeps only ~4 loads in flight per lane (ptxas interleaves
+        // loads and FMAs) and is L2-latency bound at ~60 us per 512 x 512 layer (measured).
+        float* wsl = ws_all + warp * 4 * K;
+        for (int c = lane; c < K; c += 32) {          // c: 16-byte chunk index over the 4 rows (K / 4 chunks per row)
+          const int r = c / (K >> 2), kc = c - r * (K >> 2);
+          const float* src = (r == 0 ? w0 : (r == 1 ? w1 : (r == 2 ? w2 : w3))) + 4 * kc;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(wsl + r * K + 4 * kc)), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
 #pragma unroll 4
-        for (int k = 0; k < K; k += 4) {   // 16 independent 16-byte weight loads in flight per lane (the loop is L2-latency bound)
-          const float4 a0 = __ldg(reinterpret_cast<const float4*>(w0 + k));
-          const float4 a1 = __ldg(reinterpret_cast<const float4*>(w1 + k));
-          const float4 a2 = __ldg(reinterpret_cast<const float4*>(w2 + k));
-          const float4 a3 = __ldg(reinterpret_cast<const float4*>(w3 + k));
-          const float x0 = xs[(k + 0) * 32 + lane], x1 = xs[(k + 1) * 32 + lane], x2 = xs[(k + 2) * 32 + lane], x3 = xs[(k + 3) * 32 + lane];
+        for (int k = 0; k < K; k += 4) {
+          const float4 a0 = *reinterpret_cast<const float4*>(wsl + k);
+          const float4 a1 = *reinterpret_cast<const float4*>(wsl + K + k);
+          const float4 a2 = *reinterpret_cast<const float4*>(wsl + 2 * K + k);
+          const float4 a3 = *reinterpret_cast<const float4*>(wsl + 3 * K + k);
+          const float x0 = xs[(k + 0) * kXsPitch + lane], x1 = xs[(k + 1) * kXsPitch + lane], x2 = xs[(k + 2) * kXsPitch + lane], x3 = xs[(k + 3) * kXsPitch + lane];
           acc[0] = fmaf(a0.x, x0, fmaf(a0.y, x1, fmaf(a0.z, x2, fmaf(a0.w, x3, acc[0]))));
           acc[1] = fmaf(a1.x, x0, fmaf(a1.y, x1, fmaf(a1.z, x2, fmaf(a1.w, x3, acc[1]))));
           acc[2] = fmaf(a2.x, x0, fmaf(a2.y, x1, fmaf(a2.z, x2, fmaf(a2.w, x3, acc[2]))));
           acc[3] = fmaf(a3.x, x0, fmaf(a3.y, x1, fmaf(a3.z, x2, fmaf(a3.w, x3, acc[3]))));
         }
+        __syncwarp();                                  // the slab is rewritten by this warp's next group
       } else {
         // a pass that straddles two input slices (never the case for the generator's tables): read x from global
         for (int r = 0; r < 4; ++r) {
@@ -126,14 +156,14 @@ int launch_linear(float* y, int64_t y_stride, const float* x, int64_t x_stride, 
                   const float* W, const float* bias, int B, int N, int K, float wscale, float bscale,
                   int act, float alpha, float gain, cudaStream_t st) {
   if (B == 0 || N == 0) return L2I_OK;
-  const size_t bt_smem = (size_t)K * 32 * sizeof(float);
+  const size_t bt_smem = ((((size_t)K * kXsPitch + 3) & ~(size_t)3) + (size_t)K * 4 * kLinBtWarps) * sizeof(float);
   // taken for EVERY batch size (not only the large ones): the summation order must not depend on the batch, image i of a
   // batch is bit-identical to the same latent run alone (tests/test_gpu_generator.py::test_large_batch_matches_single_sample_runs)
   static const bool bt_off = std::getenv("L2I_LINEAR_BT") != nullptr && std::atoi(std::getenv("L2I_LINEAR_BT")) == 0;   // debug A/B
-  if (!bt_off && K % 4 == 0 && bt_smem <= 96 * 1024 && ((uintptr_t)W % 16 == 0)) {
+  if (!bt_off && K % 4 == 0 && bt_smem <= 200 * 1024 && ((uintptr_t)W % 16 == 0) && ((uintptr_t)x % 16 == 0) && x_stride % 4 == 0) {
     static bool attr_set = false;
     if (!attr_set) {
-      L2I_CUDA_TRY(cudaFuncSetAttribute(linear_bt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      L2I_CUDA_TRY(cudaFuncSetAttribute(linear_bt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr_set = true;
     }
     const int groups = (N + 3) / 4;

@@ -115,10 +115,196 @@ __global__ void __launch_bounds__(256) upfirdn2d_planar_kernel(T* __restrict__ y
   }
 }
 
+// ---- 4 x 4 kernels with up, down in {1, 2} (the reference's modes 1, 3, 5: Blur, Upsample, Downsample / their transposes) -----
+// op/upfirdn2d_kernel.cu:177-211.  A CTA owns a 32 x 128 output tile: the input footprint is staged once in shared memory
+// (coalesced loads, zero fill outside the image = the op's padding), every thread produces 4 adjacent outputs of 4 rows from a
+// register window of the footprint rows (7 / 10 / 3 shared-memory loads per 4 outputs and tap row instead of 16), all index
+// arithmetic (the op's floor divisions) is hoisted out of the pixel loops, taps live in registers (up = 1) or are read as
+// broadcast LDS (up = 2), and the 4 outputs leave as one 16- or 8-byte store.
+constexpr int kP4TileH = 32, kP4TileW = 128;
+
+template <typename T> struct OutVec4;
+template <> struct OutVec4<float> {
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+  static constexpr int kAlign = 16;
+};
+template <> struct OutVec4<__nv_bfloat16> {
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[4]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+  }
+  static constexpr int kAlign = 8;
+};
+template <> struct OutVec4<__half> {
+  static __device__ __forceinline__ void store(__half* p, const float (&v)[4]) {
+    __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+  }
+  static constexpr int kAlign = 8;
+};
+
+template <typename T, int UP, int DOWN>
+__global__ void __launch_bounds__(256) upfirdn2d_planar4_kernel(T* __restrict__ y, const T* __restrict__ x,
+                                                                const float* __restrict__ kernel, UpfirdnParams p,
+                                                                int tiles_x, int tiles_y, int fh, int fw) {
+  extern __shared__ float smem[];
+  float* sk = smem;        // 16 flipped taps
+  float* sx = smem + 16;   // fh x fw input footprint
+  if (threadIdx.x < 16) sk[threadIdx.x] = kernel[15 - threadIdx.x];   // flip both axes of the 4 x 4 kernel
+  constexpr int NT = 4 / UP;                 // taps per axis that hit a real input sample
+  constexpr int SPAN = (3 * DOWN) / UP + NT + (UP > 1 ? 1 : 0);   // footprint columns touched by 4 adjacent outputs
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t tiles_per_plane = (int64_t)tiles_x * tiles_y;
+  const int64_t ntiles = tiles_per_plane * p.major;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t plane = tile / tiles_per_plane;
+    const int tr = (int)(tile - plane * tiles_per_plane);
+    const int tyi = tr / tiles_x, txi = tr - tyi * tiles_x;
+    const int oy0 = tyi * kP4TileH, ox0 = txi * kP4TileW;
+    const int mid_y0 = oy0 * DOWN + UP - 1 - p.pad_y0;
+    const int mid_x0 = ox0 * DOWN + UP - 1 - p.pad_x0;
+    const int in_y_base = floor_div_i(mid_y0, UP);
+    const int in_x_base = floor_div_i(mid_x0, UP);
+    const T* xp = x + plane * (int64_t)p.in_h * p.in_w;
+    __syncthreads();
+    for (int ry = ty; ry < fh; ry += 8) {
+      const int iy = in_y_base + ry;
+      const bool rok = iy >= 0 && iy < p.in_h;
+      const T* xr = xp + (int64_t)iy * p.in_w;
+      for (int rx = tx; rx < fw; rx += 32) {
+        const int ix = in_x_base + rx;
+        sx[ry * fw + rx] = (rok && ix >= 0 && ix < p.in_w) ? to_f32<T>(xr[ix]) : 0.f;
+      }
+    }
+    __syncthreads();
+    // this thread's 4 adjacent output columns: first footprint column and first tap of each
+    int cx[4], kx0[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int mid_x = mid_x0 + (4 * tx + j) * DOWN;
+      const int in_x = floor_div_i(mid_x, UP);
+      kx0[j] = (in_x + 1) * UP - mid_x - 1;
+      cx[j] = in_x - in_x_base;
+    }
+    float kreg[16];
+    if (UP == 1) {
+#pragma unroll
+      for (int t = 0; t < 16; ++t) kreg[t] = sk[t];
+    }
+    T* yp = y + plane * (int64_t)p.out_h * p.out_w;
+    const int ox = ox0 + 4 * tx;
+    if (UP == 1) {
+      // 4 x 4 output block per thread: each footprint row is read once into a register window and feeds up to four output rows
+      // (49 / 100 shared-memory loads per 16 outputs for down = 1 / 2 instead of 112 / 160)
+      constexpr int RSPAN = 3 * DOWN + 4;
+      const int oyb = oy0 + 4 * ty;
+      if (oyb < p.out_h && ox < p.out_w) {
+        const float* srow = sx + (4 * ty * DOWN) * fw + cx[0];      // in_y - in_y_base = ry * DOWN for up = 1
+        float acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[a][j] = 0.f;
+#pragma unroll
+        for (int r = 0; r < RSPAN; ++r) {
+          float win[SPAN];
+#pragma unroll
+          for (int c = 0; c < SPAN; ++c) win[c] = srow[r * fw + c];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            const int t = r - a * DOWN;                              // tap row of output row a (compile time)
+            if (t >= 0 && t < 4) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) acc[a][j] = fmaf(win[j * DOWN + u], kreg[t * 4 + u], acc[a][j]);
+            }
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int oy = oyb + a;
+          if (oy >= p.out_h) break;
+          T* dst = yp + (int64_t)oy * p.out_w + ox;
+          if (ox + 3 < p.out_w && ((uintptr_t)dst % OutVec4<T>::kAlign) == 0) {
+            OutVec4<T>::store(dst, acc[a]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (ox + j < p.out_w) dst[j] = from_f32<T>(acc[a][j]);
+          }
+        }
+      }
+      continue;
+    }
+#pragma unroll
+    for (int rr = 0; rr < kP4TileH / 8; ++rr) {
+      const int ry = ty + 8 * rr;
+      const int oy = oy0 + ry;
+      if (oy >= p.out_h || ox >= p.out_w) continue;
+      const int mid_y = mid_y0 + ry * DOWN;
+      const int in_y = floor_div_i(mid_y, UP);
+      const int ky0 = (in_y + 1) * UP - mid_y - 1;
+      const float* srow = sx + (in_y - in_y_base) * fw + cx[0];
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        float win[SPAN];
+#pragma unroll
+        for (int c = 0; c < SPAN; ++c) win[c] = srow[t * fw + c];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int u = 0; u < NT; ++u) {
+            // up = 2: column offset and first tap depend on the parity of mid_x (runtime, fixed per thread and j)
+            const int off = cx[j] - cx[0] + u;
+            float v = win[0];
+#pragma unroll
+            for (int c = 1; c < SPAN; ++c) v = off == c ? win[c] : v;
+            acc[j] = fmaf(v, sk[(ky0 + t * UP) * 4 + kx0[j] + u * UP], acc[j]);
+          }
+        }
+      }
+      T* dst = yp + (int64_t)oy * p.out_w + ox;
+      if (ox + 3 < p.out_w && ((uintptr_t)dst % OutVec4<T>::kAlign) == 0) {
+        OutVec4<T>::store(dst, acc);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (ox + j < p.out_w) dst[j] = from_f32<T>(acc[j]);
+      }
+    }
+  }
+}
+
+template <typename T, int UP, int DOWN>
+static int launch_planar4(void* y, const void* x, const float* kernel, const UpfirdnParams& p, cudaStream_t st) {
+  const int fh = ((kP4TileH - 1) * DOWN + 3) / UP + 2;
+  const int fw = ((kP4TileW - 1) * DOWN + 3) / UP + 2;
+  const size_t smem = sizeof(float) * (16 + (size_t)fh * fw);
+  auto kern = upfirdn2d_planar4_kernel<T, UP, DOWN>;
+  static bool attr_set = false;
+  if (!attr_set && smem > 48 * 1024) {
+    L2I_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int tiles_x = ceil_div(p.out_w, kP4TileW), tiles_y = ceil_div(p.out_h, kP4TileH);
+  const int64_t ntiles = (int64_t)tiles_x * tiles_y * p.major;
+  const int per_sm = smem > 48 * 1024 ? 3 : 8;
+  const int blocks = (int)std::min<int64_t>(ntiles, (int64_t)kNumSMs * per_sm);
+  kern<<<blocks, 256, smem, st>>>((T*)y, (const T*)x, kernel, p, tiles_x, tiles_y, fh, fw);
+  return check_launch("upfirdn2d_planar4");
+}
+
 template <typename T>
 static int launch_upfirdn(void* y, const void* x, const float* kernel, const UpfirdnParams& p, cudaStream_t st) {
   const int64_t total = p.major * p.out_h * (int64_t)p.out_w * p.minor;
   if (total == 0) return L2I_OK;
+  if (p.minor == 1 && p.kh == 4 && p.kw == 4 && p.up_x == p.up_y && p.down_x == p.down_y) {
+    if (p.up_x == 1 && p.down_x == 1) return launch_planar4<T, 1, 1>(y, x, kernel, p, st);
+    if (p.up_x == 2 && p.down_x == 1) return launch_planar4<T, 2, 1>(y, x, kernel, p, st);
+    if (p.up_x == 1 && p.down_x == 2) return launch_planar4<T, 1, 2>(y, x, kernel, p, st);
+  }
   if (p.minor == 1) {
     const int fh = ((kTileH - 1) * p.down_y + p.kh - 1) / p.up_y + 2;
     const int fw = ((kTileW - 1) * p.down_x + p.kw - 1) / p.up_x + 2;

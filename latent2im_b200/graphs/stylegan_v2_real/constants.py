@@ -24,4 +24,6 @@ allow_random_init = os.environ.get("L2I_ALLOW_RANDOM_INIT", "0") not in ("0", ""
 compute_dtype = "fp32" if os.environ.get("L2I_DTYPE", "bf16").lower() in ("fp32", "f32", "float32") else "bf16"
 walk_is_mlp = False
 # stock ResNet-50 regressor under bf16 autocast + channels_last (train.py --amp); False = the reference's fp32 arithmetic
+# fold the frozen eval-mode BatchNorms of the regressor into its convolutions (exact up to fp32 rounding; L2I_REG_FOLD_BN=0 disables)
+reg_fold_bn = os.environ.get("L2I_REG_FOLD_BN", "1") not in ("0", "")
 reg_amp = os.environ.get("L2I_REG_AMP", "0") not in ("0", "")

@@ -355,6 +355,9 @@ class TransformGraph:
         else:
             _missing_checkpoint("attribute regressor", constants.reg_path)
         model = model.to(self.device).eval()
+        if getattr(constants, "reg_fold_bn", True):
+            from latent2im_b200.regressor import fold_batchnorm
+            model = fold_batchnorm(model, inplace=True)   # frozen eval-mode BN == constant affine map: folded into the convs
         if getattr(constants, "reg_amp", False):
             model = model.to(memory_format=torch.channels_last)
         for p in model.parameters():

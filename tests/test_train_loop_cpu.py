@@ -105,3 +105,33 @@ def test_multi_attr_loop_targets_losses_and_rank_sharding(tmp_path):
     train.train_loop(g1, _opt(tmp_path / "r1", epochs=1), consts, _graph_util(), ["night", "dark"], rank=1, world=2, multi_attr=True)
     assert len(g1.calls) == 12 // 6
     assert torch.equal(g1.calls[0]["org"], g.calls[1]["org"])
+
+
+def test_regressor_batchnorm_folding_preserves_values_and_input_gradients():
+    """The frozen eval-mode ResNet-50 regressor with its BatchNorms folded into the convolutions (latent2im_b200/regressor.py)
+    computes the same attribute predictions and the same gradient w.r.t. the image as the stock module."""
+    import torch
+    import torchvision
+    from latent2im_b200.regressor import fold_batchnorm
+    torch.manual_seed(0)
+    m = torchvision.models.resnet50(weights=None)
+    m.fc = torch.nn.Linear(2048, 40)
+    m.eval()
+    for mod in m.modules():          # non-trivial running statistics / affine parameters
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.1)
+            mod.running_var.uniform_(0.5, 1.5)
+            mod.weight.data.uniform_(0.5, 1.5)
+            mod.bias.data.normal_(0, 0.1)
+    f = fold_batchnorm(m)
+    assert not any(isinstance(q, torch.nn.BatchNorm2d) for q in f.modules())
+    x = torch.randn(2, 3, 64, 64)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya, yb = torch.sigmoid(m(xa)), torch.sigmoid(f(xb))
+    assert (ya - yb).abs().max().item() <= 1e-4
+    ya[:, 31].sum().backward()
+    yb[:, 31].sum().backward()
+    assert (xa.grad - xb.grad).abs().max().item() <= 1e-3 * xa.grad.abs().max().item()
+    import pytest
+    with pytest.raises(RuntimeError):
+        fold_batchnorm(m.train())
