@@ -104,10 +104,11 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   constexpr int CK = CW < 32 ? CW : 32;         // columns per tcgen05.ld / staging tile / TMA store
   constexpr int NCHK = CW / CK;                 // chunks per epilogue warp
   static_assert((EW == 8 || EW == 16) && (CK == 16 || CK == 32) && CW <= CO, "epilogue warp layout");
-  // DIRECT (16-column warps): a lane's 16 bf16 channels are one full 32-byte sector of the NHWC output, so they leave as two
-  // 16-byte global stores - no staging tile, no proxy fence (a MEMBAR that waits for every outstanding load of the thread), no
-  // TMA-store bookkeeping - and the noise value is a plain global load issued one row ahead instead of the shared-memory ring.
-  constexpr bool DIRECT = CK == 16;
+  // DIRECT (experiment, off): a lane's 16 bf16 channels are one full 32-byte sector of the NHWC output, so they could leave as two
+  // 16-byte global stores - no staging tile, no proxy fence, no TMA-store bookkeeping - with the noise value as a plain global
+  // load issued one row ahead.  Measured: 64 -> 32 layer 1.11 -> 1.31 ms (the strided 16-byte stores cost more LSU time than the
+  // staging path costs instructions), so the TMA-store path stays.
+  constexpr bool DIRECT = false;
   // launch allocation (registers per thread) and the setmaxnreg split between the producer / MMA warpgroup and the epilogue warps
   constexpr int kRegLaunch = EW == 8 ? 168 : 96, kRegLow = EW == 8 ? 48 : 32, kRegHigh = EW == 8 ? 224 : 112;
   constexpr int kSlots = 512 / N >= 8 ? 8 : 512 / N;   // TMEM accumulator ring (rows of Hb): 8 x 64 or 4 x 128 columns

@@ -115,6 +115,13 @@ int run_conv(l2i_generator* g, const StyledConvLayer& L, const void* in, const C
     set_error("generator: L2I_CONV_IMPL=tc but layer %s is not supported by the tcgen05 kernel", L.name.c_str());
     return L2I_ERR_UNSUPPORTED;
   }
+  // no tcgen05 variant takes this layer shape: say so (once per layer) instead of silently running ~20x slower on CUDA cores
+  static std::unordered_map<std::string, bool> warned;
+  if (!warned[L.name]) {
+    warned[L.name] = true;
+    std::fprintf(stderr, "l2i_b200: warning: bf16 layer %s (Cin %d, Cout %d, %dx%d -> %d) falls back to the CUDA-core conv kernel; "
+                         "set L2I_CONV_IMPL=tc to make this an error\n", L.name.c_str(), L.cin, L.cout, L.res_in, L.res_in, L.res_out);
+  }
   return launch_conv_simt<__nv_bfloat16>(in, L.w_f32, geom, e, st);
 }
 

@@ -1,4 +1,6 @@
-"""One bf16 forward + backward at 512 px (channel multiplier 1: every special tcgen05 kernel is on the path) for compute-sanitizer."""
+"""One bf16 forward + backward at 512 px (channel multiplier 1: every special tcgen05 kernel is on the path) and one bf16 forward at
+256 px (channel multiplier 2: the 256 -> 128 row-marching up-conv and the A-resident 128 -> 128 layer) for compute-sanitizer
+(--tool memcheck | racecheck | initcheck | synccheck)."""
 import os, sys
 sys.path.insert(0, os.getcwd())
 import torch
@@ -17,3 +19,11 @@ out, _ = gen(l, input_is_latent=True, noise=noise)
 out.sum().backward()
 torch.cuda.synchronize()
 print("forward/backward done", float(img.abs().mean()), float(l.grad.abs().mean()), bool(torch.equal(u8, u8b)))
+gen2 = load_synthetic(Generator(256, 512, 2), seed=1, rgb_gain=0.25).cuda().eval()
+gen2.set_native(dtype=torch.bfloat16, max_batch=1)
+z2 = torch.tensor(synthetic_z(1, 1), dtype=torch.float32).cuda()
+with torch.no_grad():
+    lat2 = gen2.style(z2)[:, None, :].repeat(1, gen2.n_latent, 1)
+    img2, _ = gen2(lat2, input_is_latent=True, noise=[n.cuda() for n in synthetic_noise(gen2.num_layers, 1)])
+torch.cuda.synchronize()
+print("256 px forward done", float(img2.abs().mean()))
