@@ -21,6 +21,7 @@
 // Work split: the (sample, channel part, column segment, input row) space is flattened and cut into gridDim.x equal
 // contiguous ranges; a range start costs three extra Hb rows (u0 = 2 m0 - 1 .. 2 m0 + 1 warm the FIR).
 #include <algorithm>
+#include <type_traits>
 
 #include "tc_epilogue.cuh"
 
@@ -87,8 +88,7 @@ __device__ __forceinline__ Run decode_run(const UprowParams& p, int64_t r, int64
 
 // CO = output channels per work unit (GEMM N = 2 * CO), KC = Cin / 64, AS = input-row ring slots,
 // BRES = weights resident (all 9 * KC planes), else streamed: BP planes of one (kh, dx) tile per stage, WST stages.
-// EW = epilogue warps: 8 (each owns one output-pixel parity = CO accumulator columns) or, for CO = 32, 16 (16 columns each): four
-// warps per scheduler instead of two hide the barrier / tcgen05.ld / shared-memory latencies of the epilogue, which bounds the layer.
+// Eight epilogue warps: (TMEM lane quadrant) x (half of the CO channels); see the epilogue for the lane -> pixel / channel map.
 template <int CO, int KC, int AS, bool BRES, int BP, int WST, int EW>
 __global__ void __launch_bounds__(128 + EW * 32, 1)
 conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
@@ -100,17 +100,12 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   constexpr int kBStageBytes = BP * kBPlaneBytes;
   constexpr int kEpiWarps = EW;
   constexpr int kThreads = 128 + EW * 32;
-  constexpr int CW = N / (EW / 4);              // accumulator columns per epilogue warp
-  constexpr int CK = CW < 32 ? CW : 32;         // columns per tcgen05.ld / staging tile / TMA store
-  constexpr int NCHK = CW / CK;                 // chunks per epilogue warp
-  static_assert((EW == 8 || EW == 16) && (CK == 16 || CK == 32) && CW <= CO, "epilogue warp layout");
-  // DIRECT (experiment, off): a lane's 16 bf16 channels are one full 32-byte sector of the NHWC output, so they could leave as two
-  // 16-byte global stores - no staging tile, no proxy fence, no TMA-store bookkeeping - with the noise value as a plain global
-  // load issued one row ahead.  Measured: 64 -> 32 layer 1.11 -> 1.31 ms (the strided 16-byte stores cost more LSU time than the
-  // staging path costs instructions), so the TMA-store path stays.
-  constexpr bool DIRECT = false;
+  constexpr int CG = CO / 2;                    // channels per epilogue warp
+  constexpr int NCHK = CG / 16;                 // 16-channel chunks per epilogue warp (one tcgen05.ld.x16 per pixel parity each)
+  constexpr bool PREG = NCHK == 1;              // the warp's per-channel vectors fit in registers
+  static_assert(EW == 8 && CG % 16 == 0, "epilogue warp layout");
   // launch allocation (registers per thread) and the setmaxnreg split between the producer / MMA warpgroup and the epilogue warps
-  constexpr int kRegLaunch = EW == 8 ? 168 : 96, kRegLow = EW == 8 ? 48 : 32, kRegHigh = EW == 8 ? 224 : 112;
+  constexpr int kRegLaunch = 168, kRegLow = 48, kRegHigh = 224;
   constexpr int kSlots = 512 / N >= 8 ? 8 : 512 / N;   // TMEM accumulator ring (rows of Hb): 8 x 64 or 4 x 128 columns
   // Vertical FIR state per epilogue thread.  NPART = 3 (CO = 32): three running partial output rows in registers, ONE
   // tcgen05.ld per Hb row, whose slot is handed back as soon as the load has landed.  NPART = 2 (CO = 64, register budget):
@@ -123,7 +118,7 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_b = smem + AS * kASlotBytes;
-  uint8_t* smem_out = smem_b + kBBytes;          // per epilogue warp: 32 pixels x CK channels (SWIZZLE_64B rows of 64 B, or plain 32 B rows)
+  uint8_t* smem_out = smem_b + kBBytes;          // per epilogue warp: two tiles (pixel parity) of 32 pixels x 16 channels, 32-byte rows
   __shared__ __align__(16) float epi_smem[3 * CO];
   __shared__ __align__(128) float noise_smem[kNoiseSlots][2 * kSegW];
   __shared__ __align__(8) uint64_t n_full[kNoiseSlots];
@@ -169,9 +164,11 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     if (lane == 0) {
       if (BRES) {
         mbar_expect_tx(&w_full[0], 9 * KC * kBPlaneBytes);
-        for (int t = 0; t < 9; ++t)
-          for (int kc = 0; kc < KC; ++kc)
-            tma_load_3d(smem_b + (t * KC + kc) * kBPlaneBytes, &tmap_w, &w_full[0], kc * 64, 0, t);
+        // resident tile order: (kh 0, dx) and (kh 1, dx) adjacent = one N = 2N operand of the paired MMAs, then the three kh 2 tiles
+        for (int t = 0; t < 9; ++t) {
+          const int kh = t / 3, dxi = t % 3;
+          tma_load_3d(smem_b + (kh < 2 ? 2 * dxi + kh : 6 + dxi) * kBPlaneBytes, &tmap_w, &w_full[0], 0, 0, t);
+        }
       }
       uint32_t acnt = 0;
       for (int64_t r = r_begin; r < r_end;) {
@@ -218,7 +215,7 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   } else if (warp == 2) {
     // ===================== noise producer: the 256-pixel fp32 noise segment of every output row, a few rows ahead ==========
     // (a global load in the epilogue threads would be waited for by the MEMBAR of every fence.proxy.async before a TMA store)
-    if (!DIRECT && lane == 0 && p.e.noise != nullptr) {
+    if (lane == 0 && p.e.noise != nullptr) {
       uint32_t ncnt = 0;
       for (int64_t r = r_begin; r < r_end;) {
         const Run q = decode_run(p, r, r_end);
@@ -256,17 +253,27 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       // K-major SWIZZLE_128B descriptor, 8-row groups 1024 B apart: only the 14-bit start-address field (bytes >> 4) changes
       constexpr uint64_t kDescHi = kmajor_desc_hi(1024, 2);
       const uint64_t b_desc0 = kmajor_desc_at(kDescHi, smem_b0);
-      // the 3 dx x KC x 4 MMAs of one (kh, input row) group; resident weights: tile (kh, dx), plane kc at a constant offset
-      auto issue_resident = [&](int kh, uint64_t a_desc, uint32_t tmem_d, uint32_t first) {
+      // Resident weights (KC = 1).  Input row m feeds Hb[2m] (kh 0) and Hb[2m+1] (kh 1): those two GEMMs share their A operand, so
+      // they are ONE N = 2N MMA into two adjacent accumulator slots (B = the adjacent (kh 0, dx) | (kh 1, dx) tiles) - the A tile,
+      // 2/3 of an N = 64 MMA's operand bytes, is read 24 instead of 36 times per input row (the shared-memory pipe bounds the layer).
+      // Hb[2m] additionally takes kh 2 of row m - 1 as N = 64 MMAs issued AFTER the pair (whose first MMA overwrites both slots).
+      constexpr uint32_t kIdescPair = make_idesc_bf16(128, 2 * N, 0);
+      auto issue_group = [&](int bslot0, int bstep, uint64_t a_desc, uint32_t tmem_d, uint32_t idesc, uint32_t first) {
 #pragma unroll
         for (int dxi = 0; dxi < 3; ++dxi)
 #pragma unroll
-          for (int kc = 0; kc < KC; ++kc)
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_bf16(tmem_d, a_desc + (uint64_t)((kc * kPlaneStride + dxi * 128 + kk * 32) >> 4),
-                        b_desc0 + (uint64_t)((((kh * 3 + dxi) * KC + kc) * kBPlaneBytes + kk * 32) >> 4), kIdesc,
-                        (first == 0 && dxi == 0 && kc == 0 && kk == 0) ? 0u : 1u);
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16(tmem_d, a_desc + (uint64_t)((dxi * 128 + kk * 32) >> 4),
+                      b_desc0 + (uint64_t)(((bslot0 + bstep * dxi) * kBPlaneBytes + kk * 32) >> 4), idesc,
+                      (first == 0 && dxi == 0 && kk == 0) ? 0u : 1u);
+      };
+      auto wait_rows = [&](uint32_t ai) {
+        while (awaited <= ai) {
+          PROF_MARK(0);
+          mbar_wait(&a_full[awaited % AS], (awaited / AS) & 1);
+          PROF_MARK(2);                                                 // 2: waiting for an input row
+          ++awaited;
+        }
       };
       // streamed weights: one ring stage (BP planes of tile (kh, dx)) per elected block
       auto issue_streamed = [&](uint64_t a_desc, uint32_t tmem_d, uint32_t first) {
@@ -294,6 +301,57 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           }
         }
       };
+      if (BRES) {
+        static_assert(!BRES || (KC == 1 && kSlots % 2 == 0), "paired MMAs: one weight plane per tile, slot pairs");
+        for (int64_t r = r_begin; r < r_end;) {
+          const Run q = decode_run(p, r, r_end);
+          // a run's first Hb row (u = 2 m0 - 1, kh 1 alone) takes an ODD slot so that every later pair (u = 2m, 2m+1) is an aligned
+          // slot pair; an even start first hands an empty slot through (the epilogue does the same)
+          if (!(tcnt & 1)) {
+            mbar_wait(&tmem_empty[tcnt % kSlots], ((tcnt / kSlots) & 1) ^ 1);
+            if (elect_one()) umma_commit(&tmem_full[tcnt % kSlots]);
+            ++tcnt;
+          }
+          {
+            const int tslot = tcnt % kSlots;
+            PROF_MARK(0);
+            mbar_wait(&tmem_empty[tslot], ((tcnt / kSlots) & 1) ^ 1);
+            PROF_MARK(1);
+            wait_rows(abase);
+            tc_fence_after();
+            const uint64_t a_m = kmajor_desc_at(kDescHi, smem_a0 + (abase % AS) * kASlotBytes);
+            if (elect_one()) {
+              issue_group(1, 2, a_m, tmem_u + (uint32_t)(tslot * N), kIdesc, 0);
+              umma_commit(&tmem_full[tslot]);
+            }
+            ++tcnt;
+          }
+          for (int j = 1; j <= q.R + 1; ++j, tcnt += 2) {
+            const int s0 = tcnt % kSlots;                     // even: Hb[2m] in slot s0, Hb[2m+1] in slot s0 + 1
+            PROF_MARK(0);                                                   // 0: issue / loop overhead
+            mbar_wait(&tmem_empty[s0], ((tcnt / kSlots) & 1) ^ 1);
+            mbar_wait(&tmem_empty[s0 + 1], ((tcnt / kSlots) & 1) ^ 1);
+            PROF_MARK(1);                                                   // 1: waiting for a free accumulator slot
+            const uint32_t ai = abase + (uint32_t)j;          // input row m; kh 2 reads row m - 1 = ai - 1, dead afterwards
+            wait_rows(ai);
+            tc_fence_after();
+            const uint64_t a_m = kmajor_desc_at(kDescHi, smem_a0 + (ai % AS) * kASlotBytes);
+            const uint64_t a_m1 = kmajor_desc_at(kDescHi, smem_a0 + ((ai - 1) % AS) * kASlotBytes);
+            const uint32_t tmem_d = tmem_u + (uint32_t)(s0 * N);
+            const bool last = j == q.R + 1;                   // the run's last input row is dead after its pair
+            if (elect_one()) {
+              issue_group(0, 2, a_m, tmem_d, kIdescPair, 0);
+              if (last) umma_commit(&a_empty[ai % AS]);
+              umma_commit(&tmem_full[s0 + 1]);
+              issue_group(6, 1, a_m1, tmem_d, kIdesc, 1);
+              umma_commit(&a_empty[(ai - 1) % AS]);
+              umma_commit(&tmem_full[s0]);
+            }
+          }
+          abase += (uint32_t)(q.R + 2);
+          r += q.R;
+        }
+      } else
       for (int64_t r = r_begin; r < r_end;) {
         const Run q = decode_run(p, r, r_end);
         const int nrows = 2 * q.R + 3;
@@ -305,45 +363,23 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           PROF_MARK(1);                                                   // 1: waiting for a free accumulator slot
           const uint32_t tmem_d = tmem_u + (uint32_t)(tslot * N);
           const uint32_t ai = abase + (uint32_t)ml;          // input row m (kh 0 / kh 1); kh 2 reads row m - 1 = ai - 1
-          while (awaited <= ai) {
-            PROF_MARK(0);
-            mbar_wait(&a_full[awaited % AS], (awaited / AS) & 1);
-            PROF_MARK(2);                                                 // 2: waiting for an input row
-            ++awaited;
-          }
+          wait_rows(ai);
           tc_fence_after();
           const uint64_t a_m = kmajor_desc_at(kDescHi, smem_a0 + (ai % AS) * kASlotBytes);
           if (k & 1) {
             // u even (py = 0): kh = 2 on row m - 1, which is dead afterwards, then kh = 0 on row m
             const uint64_t a_m1 = kmajor_desc_at(kDescHi, smem_a0 + ((ai - 1) % AS) * kASlotBytes);
-            if (BRES) {
-              if (elect_one()) {
-                issue_resident(2, a_m1, tmem_d, 0);
-                umma_commit(&a_empty[(ai - 1) % AS]);
-                issue_resident(0, a_m, tmem_d, 1);
-                umma_commit(&tmem_full[tslot]);
-              }
-            } else {
-              issue_streamed(a_m1, tmem_d, 0);
-              if (elect_one()) umma_commit(&a_empty[(ai - 1) % AS]);
-              issue_streamed(a_m, tmem_d, 1);
-              if (elect_one()) umma_commit(&tmem_full[tslot]);
-            }
+            issue_streamed(a_m1, tmem_d, 0);
+            if (elect_one()) umma_commit(&a_empty[(ai - 1) % AS]);
+            issue_streamed(a_m, tmem_d, 1);
+            if (elect_one()) umma_commit(&tmem_full[tslot]);
           } else {
             // u odd (py = 1): kh = 1 on row m; the run's last input row is dead after its kh = 1 group
             const bool last = k == nrows - 1;
-            if (BRES) {
-              if (elect_one()) {
-                issue_resident(1, a_m, tmem_d, 0);
-                if (last) umma_commit(&a_empty[ai % AS]);
-                umma_commit(&tmem_full[tslot]);
-              }
-            } else {
-              issue_streamed(a_m, tmem_d, 0);
-              if (elect_one()) {
-                if (last) umma_commit(&a_empty[ai % AS]);
-                umma_commit(&tmem_full[tslot]);
-              }
+            issue_streamed(a_m, tmem_d, 0);
+            if (elect_one()) {
+              if (last) umma_commit(&a_empty[ai % AS]);
+              umma_commit(&tmem_full[tslot]);
             }
           }
         }
@@ -357,28 +393,36 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegHigh));
     // ===================== epilogue: vertical FIR from TMEM + noise / bias / lrelu / next-style scale =====================
+    // Warp e = (TMEM lane quadrant q4, channel half): a lane owns BOTH output pixels 2n, 2n+1 of its input column n and CG = CO / 2
+    // channels, in chunks of 16.  Why: the shared-memory data pipe bounds these layers (ncu: LDS + tensor-core operand wavefronts
+    // > 90 % of its cycles) and a warp-wide LDS.128 of per-channel vectors costs 4 wavefronts even when every lane reads the same
+    // address (the pipe delivers 128 B per clock to the register file) - 12 B of parameter traffic per 4-byte accumulator element
+    // when a lane owns one pixel.  With two pixels per lane every parameter is used twice, and for CG = 16 (the 64 -> 32 layer) the
+    // three vectors stay in registers for the whole run: no parameter LDS at all.
+    // Arithmetic on packed fp32 pairs (FFMA2): out = sum_i f_i Hb_i + b/d via the state chain, y = lrelu(D out + noise) s_next.
     const EpiParams& e = p.e;
     const int ew = warp - 4;
-    const int q4 = warp & 3;                      // TMEM lane quadrant this warp may read
-    const int col0 = (ew >> 2) * CW;              // this warp's first accumulator column; columns are (parity b, channel)
-    const int hb = col0 / CO;                     // output pixel parity b
-    const int cch = col0 % CO;                    // first channel (within the work unit's CO) of this warp
-    const int etid = threadIdx.x - 128;
-    float* s_d = epi_smem;
-    float* s_b = epi_smem + CO;
-    float* s_n = epi_smem + 2 * CO;
+    const int q4 = warp & 3;                      // TMEM lane quadrant this warp may read (= hardware warp id % 4)
+    const int chalf = ew >> 2;
+    const int cch = chalf * CG;                   // first channel (within the work unit's CO) of this warp
+    const int etid = ew * 32 + lane;
+    float* s_d = epi_smem;                        // demod * sqrt2
+    float* s_b = epi_smem + CO;                   // bias / demod  (added once per output row through the FIR state)
+    float* s_n = epi_smem + 2 * CO;               // next layer's style
     constexpr float kSqrt2 = 1.4142135623730951f;
     const bool has_noise = e.noise != nullptr;
     const float nw = (has_noise && e.noise_w != nullptr) ? __ldg(e.noise_w) * kSqrt2 : 0.f;
-    const float f0 = e.fir[0], f1 = e.fir[1], f2 = e.fir[2], f3 = e.fir[3];
-    uint8_t* stage_tile = smem_out + ew * (32 * CK * 2);
-    uint4* stage_row = reinterpret_cast<uint4*>(stage_tile + lane * (CK * 2));   // this lane's pixel: CK bf16
-    const int stage_swz = CK == 32 ? ((lane >> 1) & 3) : 0;                        // SWIZZLE_64B: 16-byte piece ^= address bits [7:8]
-    const uint32_t lane_taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)col0;
-    const float* my_noise = &noise_smem[0][2 * (q4 * 32 + lane) + hb];
+    const uint64_t F0 = pk2(e.fir[0], e.fir[0]), F1 = pk2(e.fir[1], e.fir[1]), F2 = pk2(e.fir[2], e.fir[2]), F3 = pk2(e.fir[3], e.fir[3]);
+    const uint64_t P2 = pk2(0.2f, 0.2f);
+    uint8_t* stage_tile = smem_out + ew * (2 * 32 * 32);                             // [parity][32 pixels][16 channels] bf16
+    uint4* stage_row = reinterpret_cast<uint4*>(stage_tile + lane * 32);
+    const int stage_swp = (lane >> 2) & 1;
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)cch;
+    const float* my_noise = &noise_smem[0][2 * (q4 * 32 + lane)];
     PROF_DECL;
     uint32_t tcnt = 0, ncnt = 0;
-    float pa[NCHK][CK], pb[NCHK][CK], pc[NPART == 3 ? NCHK : 1][CK];
+    uint64_t st[NPART][NCHK][2][8];
+    uint64_t rD[PREG ? 8 : 1], rB[PREG ? 8 : 1], rN[PREG ? 8 : 1];
     for (int64_t r = r_begin; r < r_end;) {
       const Run q = decode_run(p, r, r_end);
       const int nrows = 2 * q.R + 3;
@@ -386,46 +430,60 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
       for (int j = etid; j < CO; j += kEpiWarps * 32) {
         const int co = q.ch * CO + j;
-        s_d[j] = (e.demod != nullptr ? __ldg(e.demod + (int64_t)q.b * e.demod_bs + co) : 1.f) * kSqrt2;
-        s_b[j] = __ldg(e.bias + co) * kSqrt2;
+        const float d = e.demod != nullptr ? __ldg(e.demod + (int64_t)q.b * e.demod_bs + co) : 1.f;
+        s_d[j] = d * kSqrt2;
+        s_b[j] = __ldg(e.bias + co) / d;
         s_n[j] = e.s_next ? __ldg(e.s_next + (int64_t)q.b * e.s_next_bs + co) : 1.f;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-      const int xo = 2 * (q.seg * kSegW + q4 * 32) + hb;                  // first output column of this warp's 32 pixels
-      const int out_W = 2 * p.W;
-      // DIRECT: this lane's pixel column in output row 0 of the sample, and its noise column
-      __nv_bfloat16* opix = (__nv_bfloat16*)e.out + (((int64_t)q.b * (2 * p.H)) * out_W + xo + 2 * lane) * p.Cout + q.ch * CO + cch;
-      const float* nptr = has_noise ? e.noise + (int64_t)q.b * e.noise_bs + xo + 2 * lane : nullptr;
-      float nz_raw = 0.f;
-      if (DIRECT && has_noise) nz_raw = __ldg(nptr + (int64_t)(2 * q.m0) * out_W);
+      if (PREG) {
 #pragma unroll
-      for (int c = 0; c < NCHK; ++c)
+        for (int j = 0; j < 8; ++j) {
+          rD[j] = *reinterpret_cast<const uint64_t*>(s_d + cch + 2 * j);
+          rB[j] = *reinterpret_cast<const uint64_t*>(s_b + cch + 2 * j);
+          rN[j] = *reinterpret_cast<const uint64_t*>(s_n + cch + 2 * j);
+        }
+      }
+      if (BRES && !(tcnt & 1)) {                                          // the empty slot in front of an even start (see the MMA issuer)
+        mbar_wait(&tmem_full[tcnt % kSlots], (tcnt / kSlots) & 1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[tcnt % kSlots]);
+        ++tcnt;
+      }
+      const int xo = 2 * (q.seg * kSegW + q4 * 32);                       // first output column of this warp's 64 pixels
 #pragma unroll
-        for (int j = 0; j < CK; ++j) { pa[c][j] = 0.f; pb[c][j] = 0.f; if (NPART == 3) pc[c][j] = 0.f; }
+      for (int t = 0; t < NPART; ++t)
+#pragma unroll
+        for (int c = 0; c < NCHK; ++c)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) st[t][c][0][j] = st[t][c][1][j] = 0ull;
 
-      // Hb row u = 2 m0 - 1 + k.  Invariant before row k:  pa = f0 H[k-3] + f1 H[k-2] + f2 H[k-1]  (output row k-2 minus its last
-      // term),  pb = f0 H[k-2] + f1 H[k-1],  pc = f0 H[k-1]  (rows before the run's first count as absent: those output rows
-      // belong to the previous range and are not written here).
-      for (int k = 0; k < nrows; ++k, ++tcnt) {
+      // Hb row u = 2 m0 - 1 + k.  Invariant before row k:  pa = f0 H[k-3] + f1 H[k-2] + f2 H[k-1] + b/d  (output row k-2 minus its
+      // last term),  pb = f0 H[k-2] + f1 H[k-1] + b/d,  pc = f0 H[k-1] + b/d  (rows before the run's first count as absent: those
+      // output rows belong to the previous range and are not written here).
+      // The FIR state rotates through NPART register sets (ROT = k mod NPART, compile time): every update is in place, where a loop
+      // with renamed pa <- pb <- pc costs one register move per state element per row.
+      auto row_step = [&](auto rot_c, const int k) {
+        constexpr int ROT = decltype(rot_c)::value;
+        constexpr int RA = ROT % NPART, RB = (ROT + 1) % NPART, RC = (ROT + 2) % NPART;
+        (void)RC;
         const int oy = 2 * q.m0 + k - 3;                                  // output row finished by Hb row k
         const bool fin = k >= 3;
-        float nz = 0.f;
-        if (DIRECT) {
-          nz = nw * nz_raw;                                               // loaded one row ago
-          if (has_noise && k >= 2 && k + 1 < nrows) nz_raw = __ldg(nptr + (int64_t)(oy + 1) * out_W);
-        }
         PROF_MARK(0);                                                     // 0: arithmetic, staging stores, TMA store issue
         mbar_wait(&tmem_full[tcnt % kSlots], (tcnt / kSlots) & 1);
         PROF_MARK(1);                                                     // 1: waiting for the Hb row (MMA)
         tc_fence_after();
         const uint32_t t_u = lane_taddr + (uint32_t)((tcnt % kSlots) * N);
         const uint32_t t_u1 = lane_taddr + (uint32_t)(((tcnt + kSlots - 1) % kSlots) * N);
-        if (!DIRECT && fin && has_noise) {                                // this row's noise segment (bulk-copied by warp 2)
+        uint64_t NZ[2] = {0ull, 0ull};
+        if (fin && has_noise) {                                           // this row's noise segment (bulk-copied by warp 2)
           const int slot = ncnt % kNoiseSlots;
           PROF_MARK(0);
           mbar_wait(&n_full[slot], (ncnt / kNoiseSlots) & 1);
           PROF_MARK(2);                                                   // 2: waiting for the noise row
-          nz = nw * my_noise[slot * 2 * kSegW];
+          const float2 nz2 = *reinterpret_cast<const float2*>(my_noise + slot * 2 * kSegW);
+          NZ[0] = pk2(nw * nz2.x, nw * nz2.x);
+          NZ[1] = pk2(nw * nz2.y, nw * nz2.y);
           // hand the slot back only after the load has been PERFORMED: an mbarrier.arrive orders nothing but the issue of the earlier
           // LDS (ptxas even schedules the arrive ahead of the load's first use), and the producer refills the slot at once (DESIGN
           // section 10; this raced once the producers' timing changed: the noise of row + 4 in a handful of pixels, caught by the
@@ -437,88 +495,127 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         }
 #pragma unroll
         for (int c = 0; c < NCHK; ++c) {
-          uint32_t v[CK], v1[NPART == 2 ? CK : 1];
-          tmem_ld_n<CK>(t_u + c * CK, v);
-          if (NPART == 2) {
-            if (k > 0) {
-              uint32_t w1[CK];
-              tmem_ld_n<CK>(t_u1 + c * CK, w1);
-#pragma unroll
-              for (int j = 0; j < CK; ++j) v1[j] = w1[j];
-            } else {
-#pragma unroll
-              for (int j = 0; j < CK; ++j) v1[j] = 0u;
-            }
-          }
+          uint32_t v[2][16];
+          tmem_ld16(t_u + c * 16, v[0]);
+          tmem_ld16(t_u + CO + c * 16, v[1]);
           PROF_MARK(0);
           tmem_ld_wait();
           PROF_MARK(3);                                                   // 3: tcgen05.ld latency
-          if (c == NCHK - 1) {
-            // NPART 3: Hb[k] is in registers, nothing will read its slot again.  NPART 2: Hb[k-1] has been read for the last time
-            // (the run's last row additionally frees its own slot).
+          if (NPART == 3 && c == NCHK - 1) {
+            // Hb[k] is in registers, nothing will read its slot again
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
-              if (NPART == 3) {
-                mbar_arrive(&tmem_empty[tcnt % kSlots]);
-              } else {
-                if (k > 0) mbar_arrive(&tmem_empty[(tcnt + kSlots - 1) % kSlots]);
-                if (k == nrows - 1) mbar_arrive(&tmem_empty[tcnt % kSlots]);
-              }
-            }
+            if (lane == 0) mbar_arrive(&tmem_empty[tcnt % kSlots]);
           }
           if (fin) {
-            // y = lrelu(d * out + noise + bias) * sqrt2 (sqrt2 folded into d, bias, noise), stored as bf16 of y * s_next
-            uint32_t packed[CK / 2];
-            const float* pd = s_d + cch + c * CK;
-            const float* pbias = s_b + cch + c * CK;
-            const float* pn = s_n + cch + c * CK;
+            PROF_MARK(0);
+            if (lane == 0) tma_store_wait_read();           // the previous stores have finished reading the staging tiles
+            __syncwarp();
+            PROF_MARK(4);                                                 // 4: previous TMA store still reading the staging tile
+            uint32_t packed[2][8];
 #pragma unroll
-            for (int j4 = 0; j4 < CK; j4 += 4) {
-              const float4 d4 = *reinterpret_cast<const float4*>(pd + j4);
-              const float4 b4 = *reinterpret_cast<const float4*>(pbias + j4);
-              const float4 n4 = *reinterpret_cast<const float4*>(pn + j4);
-              const float dd[4] = {d4.x, d4.y, d4.z, d4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w}, nn[4] = {n4.x, n4.y, n4.z, n4.w};
-              float x[4];
-#pragma unroll
-              for (int h = 0; h < 4; ++h) {
-                const float o = fmaf(f3, __uint_as_float(v[j4 + h]), pa[c][j4 + h]);
-                x[h] = fmaf(o, dd[h], bb[h] + nz);
-                x[h] = fmaxf(x[h], 0.2f * x[h]) * nn[h];
+            for (int j = 0; j < 8; j += 2) {                // four channels of both pixels per parameter fetch
+              uint64_t D[2], NN[2];
+              if (PREG) {
+                D[0] = rD[j]; D[1] = rD[j + 1]; NN[0] = rN[j]; NN[1] = rN[j + 1];
+              } else {
+                const ulonglong2 d2 = *reinterpret_cast<const ulonglong2*>(s_d + cch + c * 16 + 2 * j);
+                const ulonglong2 n2 = *reinterpret_cast<const ulonglong2*>(s_n + cch + c * 16 + 2 * j);
+                D[0] = d2.x; D[1] = d2.y; NN[0] = n2.x; NN[1] = n2.y;
               }
-              packed[j4 >> 1] = pack_bf16(x[0], x[1]);
-              packed[(j4 >> 1) + 1] = pack_bf16(x[2], x[3]);
+#pragma unroll
+              for (int par = 0; par < 2; ++par)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const uint64_t X = pk2u(v[par][2 * (j + h)], v[par][2 * (j + h) + 1]);
+                  const uint64_t o = fma2(F3, X, st[RA][c][par][j + h]);
+                  const uint64_t y = fma2(o, D[h], NZ[par]);
+                  const uint64_t m = mul2(y, P2);
+                  float y0, y1, m0, m1;
+                  upk2(y, y0, y1);
+                  upk2(m, m0, m1);
+                  const uint64_t z = mul2(pk2(fmaxf(y0, m0), fmaxf(y1, m1)), NN[h]);   // lrelu(y) * s_next
+                  float z0, z1;
+                  upk2(z, z0, z1);
+                  packed[par][j + h] = pack_bf16(z0, z1);
+                }
             }
-            if (DIRECT) {
-              uint4* dst = reinterpret_cast<uint4*>(opix + (int64_t)oy * out_W * p.Cout + c * CK);
 #pragma unroll
-              for (int kq = 0; kq < CK / 8; ++kq) dst[kq] = make_uint4(packed[4 * kq], packed[4 * kq + 1], packed[4 * kq + 2], packed[4 * kq + 3]);
+            for (int par = 0; par < 2; ++par) {
+              // 32-byte rows at 32-byte lane pitch: lanes 4-7 of every eight write their upper 16 bytes first, so that one STS.128
+              // touches eight different 16-byte bank groups (plain order: 14 wavefronts per store measured instead of 4)
+              const uint4 lo = make_uint4(packed[par][0], packed[par][1], packed[par][2], packed[par][3]);
+              const uint4 hi = make_uint4(packed[par][4], packed[par][5], packed[par][6], packed[par][7]);
+              stage_row[par * 64 + stage_swp] = stage_swp ? hi : lo;
+              stage_row[par * 64 + (stage_swp ^ 1)] = stage_swp ? lo : hi;
+            }
+            PROF_MARK(0);
+            fence_proxy_async_smem();
+            __syncwarp();
+            PROF_MARK(5);                                                 // 5: proxy fence (MEMBAR) before the TMA store
+            if (lane == 0) {
+              tma_store_4d_nocommit(&tmap_o, stage_tile, q.ch * CO + cch + c * 16, xo, oy, q.b);
+              tma_store_4d(&tmap_o, stage_tile + 1024, q.ch * CO + cch + c * 16, xo + 1, oy, q.b);
+            }
+          }
+          // next row: pa' = f2 X + pb (set RB), pb' = f1 X + pc (set RC) or f1 X + f0 X1 + b/d, pc' = f0 X + b/d (set RA)
+          uint64_t BQ[8];
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            if (PREG) {
+              BQ[j] = rB[j]; BQ[j + 1] = rB[j + 1];
             } else {
-              PROF_MARK(0);
-              if (lane == 0) tma_store_wait_read();         // the previous store has finished reading the staging tile
-              __syncwarp();
-              PROF_MARK(4);                                               // 4: previous TMA store still reading the staging tile
-#pragma unroll
-              for (int kq = 0; kq < CK / 8; ++kq)
-                stage_row[kq ^ stage_swz] = make_uint4(packed[4 * kq], packed[4 * kq + 1], packed[4 * kq + 2], packed[4 * kq + 3]);
-              PROF_MARK(0);
-              fence_proxy_async_smem();
-              __syncwarp();
-              PROF_MARK(5);                                               // 5: proxy fence (MEMBAR) before the TMA store
-              if (lane == 0) tma_store_4d(&tmap_o, stage_tile, q.ch * CO + cch + c * CK, xo, oy, q.b);
+              const ulonglong2 b2 = *reinterpret_cast<const ulonglong2*>(s_b + cch + c * 16 + 2 * j);
+              BQ[j] = b2.x; BQ[j + 1] = b2.y;
             }
           }
 #pragma unroll
-          for (int j = 0; j < CK; ++j) {
-            const float x = __uint_as_float(v[j]);
-            pa[c][j] = fmaf(f2, x, pb[c][j]);
-            if (NPART == 3) {
-              pb[c][j] = fmaf(f1, x, pc[c][j]);
-              pc[c][j] = f0 * x;
-            } else {
-              pb[c][j] = fmaf(f1, x, f0 * __uint_as_float(v1[j]));
+          for (int par = 0; par < 2; ++par) {
+            uint32_t v1[16];
+            if (NPART == 2) {                               // Hb[k-1] again (register budget: no third state set for 64 channels)
+              if (k > 0) {
+                tmem_ld16(t_u1 + par * CO + c * 16, v1);
+                tmem_ld_wait();
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v1[j] = 0u;
+              }
+              if (c == NCHK - 1 && par == 1) {
+                // Hb[k-1] has been read for the last time (the run's last row additionally frees its own slot)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                  if (k > 0) mbar_arrive(&tmem_empty[(tcnt + kSlots - 1) % kSlots]);
+                  if (k == nrows - 1) mbar_arrive(&tmem_empty[tcnt % kSlots]);
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint64_t X = pk2u(v[par][2 * j], v[par][2 * j + 1]);
+              st[RB][c][par][j] = fma2(F2, X, st[RB][c][par][j]);
+              if (NPART == 3) {
+                st[RC][c][par][j] = fma2(F1, X, st[RC][c][par][j]);
+                st[RA][c][par][j] = fma2(F0, X, BQ[j]);
+              } else {
+                st[RA][c][par][j] = fma2(F1, X, fma2(F0, pk2u(v1[2 * j], v1[2 * j + 1]), BQ[j]));
+              }
             }
           }
+        }
+      };
+      for (int k = 0; k < nrows;) {
+        row_step(std::integral_constant<int, 0>{}, k);
+        ++tcnt;
+        if (++k >= nrows) break;
+        row_step(std::integral_constant<int, 1>{}, k);
+        ++tcnt;
+        ++k;
+        if (NPART == 3) {
+          if (k >= nrows) break;
+          row_step(std::integral_constant<int, 2 % NPART>{}, k);
+          ++tcnt;
+          ++k;
         }
       }
       r += q.R;
@@ -539,8 +636,7 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 template <int CO, int KC, int AS, bool BRES, int BP, int WST, int EW>
 int launch_uprow_variant(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const UprowParams& p, cudaStream_t st) {
   constexpr int N = 2 * CO;
-  constexpr int CK = (N / (EW / 4)) < 32 ? (N / (EW / 4)) : 32;
-  constexpr int smem = AS * KC * kPlaneStride + (BRES ? 9 * KC : WST * BP) * N * 128 + EW * 32 * CK * 2 + 1024;
+  constexpr int smem = AS * KC * kPlaneStride + (BRES ? 9 * KC : WST * BP) * N * 128 + EW * 2048 + 1024;
   static_assert(smem + 3 * CO * 4 + kNoiseSlots * 1024 + 512 <= 227 * 1024, "shared memory budget (dynamic + static)");
   auto kern = conv_tc_uprow_kernel<CO, KC, AS, BRES, BP, WST, EW>;
   static bool attr_set = false;
@@ -625,16 +721,14 @@ int launch_conv_tc_uprow(const void* in, const __nv_bfloat16* w, const ConvGeom&
     L2I_TRY(make_tmap(&tw, w, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
   }
   {
-    // output NHWC [B][2H][2W][Cout] bf16; an epilogue warp stores 32 channels of every other pixel of 64 consecutive pixels
+    // output NHWC [B][2H][2W][Cout] bf16; an epilogue warp stores 16 channels of every other pixel of 64 consecutive pixels (one store per pixel parity)
     const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)(2 * g.W), (uint64_t)(2 * g.H), (uint64_t)g.B};
     const uint64_t str[4] = {2, (uint64_t)Cout * 2, (uint64_t)2 * g.W * Cout * 2, (uint64_t)4 * g.H * g.W * Cout * 2};
-    // (the 16-warp variant stores 16 channels = 32-byte rows, no swizzle)
-    const uint32_t ck = CO == 32 ? 16 : 32;
-    const uint32_t box[4] = {ck, 64, 1, 1};
+    const uint32_t box[4] = {16, 64, 1, 1};
     const uint32_t estr[4] = {1, 2, 1, 1};
-    L2I_TRY(make_tmap_strided(&to, e.out, 4, dims, str, box, estr, ck == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE));
+    L2I_TRY(make_tmap_strided(&to, e.out, 4, dims, str, box, estr, CU_TENSOR_MAP_SWIZZLE_NONE));
   }
-  if (CO == 32) return launch_uprow_variant<32, 1, 4, true, 1, 1, 16>(ta, tw, to, p, st);
+  if (CO == 32) return launch_uprow_variant<32, 1, 4, true, 1, 1, 8>(ta, tw, to, p, st);
   if (g.Cin == 128) return launch_uprow_variant<64, 2, 2, false, 2, 4, 8>(ta, tw, to, p, st);
   // Cin = 256: two input rows are 136 KB, which leaves a 4 x 16 KB weight ring (one 64-channel plane per stage)
   return launch_uprow_variant<64, 4, 2, false, 1, 4, 8>(ta, tw, to, p, st);

@@ -24,6 +24,12 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+// same without closing the bulk group: several stores of one staging buffer form one group
+__device__ __forceinline__ void tma_store_4d_nocommit(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(smem_u32(src)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

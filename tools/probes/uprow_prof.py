@@ -44,9 +44,9 @@ def main():
         print(f"--- KC={kc} ({layer}) ---")
         tot = blk[:, 1, 7].mean()
         print(f"  MMA issuer: total {tot:.0f} clk/CTA; " + ", ".join(f"{nm} {100 * blk[:, 1, i].mean() / tot:.1f}%" for i, nm in enumerate(names_mma[:4])))
-        for w in range(4, 4 + (16 if kc == 1 else 8)):
+        for w in range(4, 12):
             tot = blk[:, w, 7].mean()
-            print(f"  epilogue warp {w} (quadrant {w & 3}, parity {(w - 4) >> 2}): total {tot:.0f}; " +
+            print(f"  epilogue warp {w} (quadrant {w & 3}, channel half {(w - 4) >> 2}): total {tot:.0f}; " +
                   ", ".join(f"{nm} {100 * blk[:, w, i].mean() / tot:.1f}%" for i, nm in enumerate(names_epi[:6])))
         e = blk[:, 4:, :]
         print("  slowest-vs-fastest epilogue warp 'work' clocks per CTA (mean over CTAs): "
