@@ -38,7 +38,7 @@ constexpr int kVSkipStride = (kVSkipFloats + 31) & ~31;   // 672 floats: buffers
 constexpr int kVNoiseFloats = 32 * 8;                     // the tile's 32 rows x 8 columns
 constexpr int kVThreads = 128 + kVGroups * 128;
 constexpr int kVWBytes = 9 * 64 * 128;                     // 73728: nine 64 x 64 bf16 tiles
-constexpr int kVStageOutBytes = 2048;                      // per epilogue warp: 32 pixels x 32 channels, SWIZZLE_64B (TMA store source)
+constexpr int kVStageOutBytes = 2048;                      // per epilogue warp: [parity][32 pixels][16 channels] bf16 (TMA store sources)
 constexpr int kVSmem = kVStages * kVStageBytes + kVWBytes + kVGroups * 4 * kVStageOutBytes + 1024;
 constexpr int kVTileW = 8, kVTileH = 32;
 
@@ -240,41 +240,67 @@ conv_tc_vpair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       mbar_wait(&tmem_full[acc], acc_parity);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N);
-      float rgb[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-      uint8_t* stage_tile = smem_stage_out + (warp - 4) * kVStageOutBytes;
-      __nv_bfloat16* stage_row = (__nv_bfloat16*)stage_tile + lane * 32;     // this lane's 64-byte row of the staging tile
-      const int stage_swz = (lane >> 1) & 3;                                 // SWIZZLE_64B: 16-byte chunk ^= address bits [7:8]
+      uint64_t rgb2[2][3] = {{0ull, 0ull, 0ull}, {0ull, 0ull, 0ull}};        // (even, odd channel) partial ToRGB sums of the two pixels
+      uint8_t* stage_tile = smem_stage_out + (warp - 4) * kVStageOutBytes;   // [parity][32 pixels][16 channels] bf16
+      uint4* stage_row = reinterpret_cast<uint4*>(stage_tile + lane * 32);
+      const int stage_swp = (lane >> 2) & 1;                                 // bank-conflict-free order of the two 16-byte halves
       const bool want_out = e.out != nullptr && e.s_next != nullptr;
+      const bool want_y = ok && e.y_out != nullptr;
+      const int64_t pix = ((int64_t)b * p.H + Y) * p.W + X;
 #pragma unroll 1
-      for (int cs = 0; cs < CO; cs += 32) {     // 32 channels of BOTH pixels of the pair: the per-channel vectors are fetched once
-        uint32_t v0[32], v1[32];
-        tmem_ld32(taddr + cs, v0);
-        tmem_ld32(taddr + CO + cs, v1);
+      for (int cs = 0; cs < CO; cs += 16) {     // 16 channels of BOTH pixels of the pair: every per-channel vector is fetched once
+        uint32_t v0[16], v1[16];
+        tmem_ld16(taddr + cs, v0);
+        tmem_ld16(taddr + CO + cs, v1);
         tmem_ld_wait();
-#pragma unroll
-        for (int par = 0; par < 2; ++par) {
-          __nv_bfloat16* outc = nullptr;
-          __nv_bfloat16* yc = nullptr;
-          const int64_t pix = ((int64_t)b * p.H + Y + par) * p.W + X;
-          if (ok && e.y_out != nullptr) yc = (__nv_bfloat16*)e.y_out + pix * CO + cs;
-          if (want_out && p.tma_store) {
-            if (lane == 0) tma_store_wait_read();     // the previous store has finished reading this warp's staging tile
-            __syncwarp();
-            outc = stage_row;
-          } else if (ok && want_out) {
-            outc = (__nv_bfloat16*)e.out + pix * CO + cs;
+        uint32_t o0[8], o1[8], y0v[8], y1v[8];
+        if (want_y) {
+          epilogue_pair16<true, true>(v0, v1, s_d + cs, s_b + cs, s_n + cs, s_w + cs, s_w + CO + cs, s_w + 2 * CO + cs, nzp[0], nzp[1],
+                                      rgb2[0], rgb2[1], o0, o1, y0v, y1v);
+          uint4* yd = reinterpret_cast<uint4*>((__nv_bfloat16*)e.y_out + pix * CO + cs);
+          yd[0] = make_uint4(y0v[0], y0v[1], y0v[2], y0v[3]);
+          yd[1] = make_uint4(y0v[4], y0v[5], y0v[6], y0v[7]);
+          yd = reinterpret_cast<uint4*>((__nv_bfloat16*)e.y_out + (pix + p.W) * CO + cs);
+          yd[0] = make_uint4(y1v[0], y1v[1], y1v[2], y1v[3]);
+          yd[1] = make_uint4(y1v[4], y1v[5], y1v[6], y1v[7]);
+        } else {
+          epilogue_pair16<true, false>(v0, v1, s_d + cs, s_b + cs, s_n + cs, s_w + cs, s_w + CO + cs, s_w + 2 * CO + cs, nzp[0], nzp[1],
+                                       rgb2[0], rgb2[1], o0, o1, y0v, y1v);
+        }
+        if (want_out && p.tma_store) {
+          if (lane == 0) tma_store_wait_read();       // the previous stores have finished reading this warp's staging tiles
+          __syncwarp();
+          const uint4 a_lo = make_uint4(o0[0], o0[1], o0[2], o0[3]), a_hi = make_uint4(o0[4], o0[5], o0[6], o0[7]);
+          const uint4 b_lo = make_uint4(o1[0], o1[1], o1[2], o1[3]), b_hi = make_uint4(o1[4], o1[5], o1[6], o1[7]);
+          stage_row[stage_swp] = stage_swp ? a_hi : a_lo;
+          stage_row[stage_swp ^ 1] = stage_swp ? a_lo : a_hi;
+          stage_row[64 + stage_swp] = stage_swp ? b_hi : b_lo;
+          stage_row[64 + (stage_swp ^ 1)] = stage_swp ? b_lo : b_hi;
+          // the warp's 4 pair-rows x 8 columns of one parity = every other image row: one strided TMA tensor store per parity
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d_nocommit(&tmap_o, stage_tile, cs, x0, y0 + 8 * q, b);
+            tma_store_4d(&tmap_o, stage_tile + 1024, cs, x0, y0 + 8 * q + 1, b);
           }
-          epilogue_chunk32<EPI_ACT_RGB>(par == 0 ? v0 : v1, s_d + cs, s_b + cs, s_n + cs, s_w + cs, s_w + CO + cs, s_w + 2 * CO + cs,
-                                        nzp[par], false, rgb[par][0], rgb[par][1], rgb[par][2], outc, yc,
-                                        (want_out && p.tma_store) ? stage_swz : 0);
-          if (want_out && p.tma_store) {
-            // the warp's 4 pair-rows x 8 columns of this parity = every other image row: one strided TMA tensor store
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) tma_store_4d(&tmap_o, stage_tile, cs, x0, y0 + 8 * q + par, b);
-          }
+        } else if (ok && want_out) {
+          uint4* od = reinterpret_cast<uint4*>((__nv_bfloat16*)e.out + pix * CO + cs);
+          od[0] = make_uint4(o0[0], o0[1], o0[2], o0[3]);
+          od[1] = make_uint4(o0[4], o0[5], o0[6], o0[7]);
+          od = reinterpret_cast<uint4*>((__nv_bfloat16*)e.out + (pix + p.W) * CO + cs);
+          od[0] = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+          od[1] = make_uint4(o1[4], o1[5], o1[6], o1[7]);
         }
       }
+      float rgb[2][3];
+#pragma unroll
+      for (int par = 0; par < 2; ++par)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float lo, hi;
+          upk2(rgb2[par][c], lo, hi);
+          rgb[par][c] = lo + hi;
+        }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
 
@@ -391,12 +417,12 @@ int launch_conv_tc_vpair(const void* in, const __nv_bfloat16* w, const ConvGeom&
   CUtensorMap to = ta;
   p.tma_store = 0;
   if (e.out != nullptr && e.s_next != nullptr && e.y_out == nullptr && (uintptr_t)e.out % 16 == 0) {
-    // a warp's 32 pixels of one parity: 8 columns x 4 rows, rows two apart; 32 of the 64 channels per store
+    // a warp's 32 pixels of one parity: 8 columns x 4 rows, rows two apart; 16 of the 64 channels per store
     const uint64_t dims[4] = {64, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
     const uint64_t str[4] = {2, 128, (uint64_t)g.W * 128, (uint64_t)g.H * g.W * 128};
-    const uint32_t box[4] = {32, 8, 8, 1};
+    const uint32_t box[4] = {16, 8, 8, 1};
     const uint32_t estr[4] = {1, 1, 2, 1};
-    L2I_TRY(make_tmap_strided(&to, e.out, 4, dims, str, box, estr, CU_TENSOR_MAP_SWIZZLE_64B));
+    L2I_TRY(make_tmap_strided(&to, e.out, 4, dims, str, box, estr, CU_TENSOR_MAP_SWIZZLE_NONE));
     p.tma_store = 1;
   }
   p.tiles_x = ceil_div(g.W, kVTileW); p.tiles_y = ceil_div(g.H, kVTileH);

@@ -97,5 +97,58 @@ __device__ __forceinline__ void epilogue_chunk32(const uint32_t (&v)[32], const 
   }
 }
 
+// Two pixels that share their per-channel vectors (the two rows of a vertical pair, the two tiles of a tile pair ...), 16 channels,
+// packed fp32 arithmetic.  Why pairs: a warp-wide LDS.128 of a per-channel vector costs four shared-memory wavefronts even though
+// every lane reads the same address, and with six vectors (demod, bias, next style, three ToRGB rows) the parameter traffic of a
+// one-pixel-per-lane epilogue is larger than the MMA operand traffic of the small-channel layers (ncu: LDS 43-65 % of the
+// shared-memory data pipe).  Every vector fetched here serves both pixels.
+//   y = lrelu(acc * d + noise + bias) * sqrt2 (sqrt2 folded into d, bias, noise);  o = bf16(y * s_next);  rgb[c] += wr[c] . y
+// rgb2[c] holds (even-channel, odd-channel) partial sums; the caller adds the halves.
+template <bool RGB, bool WANT_Y>
+__device__ __forceinline__ void epilogue_pair16(const uint32_t (&va)[16], const uint32_t (&vb)[16], const float* s_d, const float* s_b,
+                                                const float* s_n, const float* s_w0, const float* s_w1, const float* s_w2, float nza,
+                                                float nzb, uint64_t (&rgba)[3], uint64_t (&rgbb)[3], uint32_t (&oa)[8], uint32_t (&ob)[8],
+                                                uint32_t (&ya)[8], uint32_t (&yb)[8]) {
+  const uint64_t NZA = pk2(nza, nza), NZB = pk2(nzb, nzb), P2 = pk2(0.2f, 0.2f);
+#pragma unroll
+  for (int j4 = 0; j4 < 16; j4 += 4) {
+    const ulonglong2 d4 = *reinterpret_cast<const ulonglong2*>(s_d + j4);
+    const ulonglong2 b4 = *reinterpret_cast<const ulonglong2*>(s_b + j4);
+    const ulonglong2 n4 = *reinterpret_cast<const ulonglong2*>(s_n + j4);
+    ulonglong2 w0 = make_ulonglong2(0ull, 0ull), w1 = w0, w2 = w0;
+    if (RGB) {
+      w0 = *reinterpret_cast<const ulonglong2*>(s_w0 + j4);
+      w1 = *reinterpret_cast<const ulonglong2*>(s_w1 + j4);
+      w2 = *reinterpret_cast<const ulonglong2*>(s_w2 + j4);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint64_t D = h ? d4.y : d4.x, Bv = h ? b4.y : b4.x, Nn = h ? n4.y : n4.x;
+      const uint64_t W0 = h ? w0.y : w0.x, W1 = h ? w1.y : w1.x, W2 = h ? w2.y : w2.x;
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        const uint32_t* v = px ? vb : va;
+        const uint64_t x = fma2(pk2u(v[j4 + 2 * h], v[j4 + 2 * h + 1]), D, add2(Bv, px ? NZB : NZA));
+        const uint64_t m = mul2(x, P2);
+        float x0, x1, m0, m1;
+        upk2(x, x0, x1);
+        upk2(m, m0, m1);
+        const float y0 = fmaxf(x0, m0), y1 = fmaxf(x1, m1);   // leaky relu
+        const uint64_t y = pk2(y0, y1);
+        if (RGB) {
+          uint64_t* rgb = px ? rgbb : rgba;
+          rgb[0] = fma2(W0, y, rgb[0]);
+          rgb[1] = fma2(W1, y, rgb[1]);
+          rgb[2] = fma2(W2, y, rgb[2]);
+        }
+        float o0, o1;
+        upk2(mul2(y, Nn), o0, o1);
+        (px ? ob : oa)[(j4 >> 1) + h] = pack_bf16(o0, o1);
+        if (WANT_Y) (px ? yb : ya)[(j4 >> 1) + h] = pack_bf16(y0, y1);   // training: the unscaled activation, kept for the backward pass
+      }
+    }
+  }
+}
+
 }  // namespace tc
 }  // namespace l2i
