@@ -32,6 +32,7 @@ void refresh_kernel_switches() {
   s.fir_simt = flag("L2I_FIR_SIMT", 0) != 0;
   s.uprow = flag("L2I_UPROW", 1) != 0;
   s.uprow_mask = flag("L2I_UPROW_MASK", 7);
+  s.cluster = flag("L2I_CLUSTER", 1);
   g_switches = s;
 }
 

@@ -47,7 +47,12 @@ __device__ __forceinline__ void ares_group_sync(int group) {
 // N = GEMM N, KC = 64-channel chunks of Cin, BP = chunks per weight-ring stage (1 or KC), WST = weight ring stages,
 // COMP = composite up-conv (N = 4 phases x N/4).  The single MMA-issuing thread pays ~100 clocks of mbarrier latency per
 // ring stage; with N = 128 a 64-channel stage is only 256 tensor clocks, so those layers take whole taps (BP = KC) per stage.
-template <int N, int KC, int BP, int WST, int GROUPS, int EPI, bool COMP>
+// CL = CTAs per cluster (1 or 2).  The weight-tile sequence is the same for every output tile, so the CTAs of a cluster run their
+// weight rings in lockstep: each loads 1 / CL of every stage and TMA-multicasts it to all of them, and a stage is free again when the
+// MMAs of every CTA have read it (multicast commit).  Why: at batch 32 the 128 -> 128 layer streams 9 x 32 KB of weights per
+// 128-pixel tile = 4.7 GB per launch from L2, which alone takes the 0.58 ms the layer measured (~8 TB/s); pairs halve it.
+// Every CTA runs the same number of tiles (indices past the end: zero-filled loads, masked epilogue), or the rings would deadlock.
+template <int N, int KC, int BP, int WST, int GROUPS, int EPI, bool COMP, int CL>
 __global__ void __launch_bounds__(128 + GROUPS * 128, 1)
 conv_tc_ares_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ AresParams p) {
@@ -79,15 +84,20 @@ conv_tc_ares_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kRAStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < WST; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int s = 0; s < WST; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], CL); }
     for (int a = 0; a < GROUPS; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();      // the peers' barriers are initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t kClusterMask = (uint16_t)((1u << CL) - 1u);
+  // same trip count in every CTA; a tile index past the end decodes to sample b >= B (loads zero-filled, nothing stored)
+  const int tile_end = CL > 1 ? (int)blockIdx.x + (int)gridDim.x * ((p.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x) : p.total_tiles;
 
   auto decode = [&](int tile, int& x0, int& y0, int& b) {
     const int tx = tile % p.tiles_x;
@@ -102,7 +112,7 @@ conv_tc_ares_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase_bit = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
         int x0, y0, b;
         decode(tile, x0, y0, b);
         mbar_wait(&a_empty[stage], phase_bit ^ 1);
@@ -118,15 +128,20 @@ conv_tc_ares_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (lane == 0) {
       int ws = 0;
       uint32_t wphase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
         for (int t = 0; t < 9; ++t) {
 #pragma unroll
           for (int kc = 0; kc < KC; kc += BP) {
             mbar_wait(&w_empty[ws], wphase ^ 1);
             mbar_expect_tx(&w_full[ws], kBStageBytes);
 #pragma unroll
-            for (int j = 0; j < BP; ++j)
-              tma_load_3d(smem_b + ws * kBStageBytes + j * kBPlaneBytes, &tmap_w, &w_full[ws], (kc + j) * 64, 0, t);
+            for (int j = 0; j < BP; ++j) {
+              if (CL > 1)   // this CTA's N / CL rows of the tile, to every CTA of the cluster
+                tma_load_3d_mc(smem_b + ws * kBStageBytes + j * kBPlaneBytes + cta_rank * (N / CL) * 128, &tmap_w, &w_full[ws], (kc + j) * 64,
+                               (int)cta_rank * (N / CL), t, kClusterMask);
+              else
+                tma_load_3d(smem_b + ws * kBStageBytes + j * kBPlaneBytes, &tmap_w, &w_full[ws], (kc + j) * 64, 0, t);
+            }
             if (++ws == WST) { ws = 0; wphase ^= 1; }
           }
         }
@@ -140,7 +155,7 @@ conv_tc_ares_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t smem_a0 = smem_u32(smem), smem_b0 = smem_u32(smem_b);
       constexpr uint64_t kHiA = kmajor_desc_hi(kRW * 128, 2), kHiB = kmajor_desc_hi(1024, 2);
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
         mbar_wait(&tmem_empty[grp], grp_phase ^ 1);
         mbar_wait(&a_full[stage], phase_bit);
         tc_fence_after();
@@ -163,7 +178,8 @@ conv_tc_ares_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                   umma_bf16(tmem_d, a_desc + (uint64_t)((j * kRPlaneStride + k * 32) >> 4), b_desc + (uint64_t)((j * kBPlaneBytes + k * 32) >> 4),
                             p.idesc, (t | kc | j | k) != 0 ? 1u : 0u);
               }
-              umma_commit(&w_empty[ws]);
+              if (CL > 1) umma_commit_mc(&w_empty[ws], kClusterMask);
+              else umma_commit(&w_empty[ws]);
             }
             if (++ws == WST) { ws = 0; wphase ^= 1; }
           }
@@ -195,14 +211,14 @@ conv_tc_ares_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint32_t grp_phase = 0;
     int staged_b = -1;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
       if (it % GROUPS != group) continue;
       int x0, y0, b;
       decode(tile, x0, y0, b);
       const int ox = x0 + lx, oy = y0 + ly;
-      const bool ok = ox < p.W && oy < p.H;
+      const bool ok = ox < p.W && oy < p.H && b < p.B;
 
-      if (b != staged_b) {
+      if (b != staged_b && b < p.B) {
         ares_group_sync(group);
         for (int j = gtid; j < CO; j += 128) {
           s_d[j] = (e.demod != nullptr ? __ldg(e.demod + (int64_t)b * e.demod_bs + j) : 1.f) * kSqrt2;
@@ -277,24 +293,35 @@ conv_tc_ares_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();      // no CTA leaves while a peer may still multicast into it or arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
 }
 
-template <int N, int KC, int BP, int WST, int GROUPS, int EPI, bool COMP>
+template <int N, int KC, int BP, int WST, int GROUPS, int EPI, bool COMP, int CL>
 int launch_ares_variant(const CUtensorMap& ta, const CUtensorMap& tw, const AresParams& p, cudaStream_t st) {
   constexpr int smem = kRAStages * KC * kRPlaneStride + WST * BP * N * 128 + 1024;
   static_assert(smem + GROUPS * 6 * (COMP ? N / 4 : N) * 4 + 512 <= 227 * 1024, "shared memory budget (dynamic + static epilogue vectors)");
-  auto kern = conv_tc_ares_kernel<N, KC, BP, WST, GROUPS, EPI, COMP>;
+  auto kern = conv_tc_ares_kernel<N, KC, BP, WST, GROUPS, EPI, COMP, CL>;
   static bool attr_set = false;
   if (!attr_set) {
     L2I_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  const int grid = std::min(p.total_tiles, kNumSMs);
-  kern<<<grid, 128 + GROUPS * 128, smem, st>>>(ta, tw, p);
+  const int grid = std::min(p.total_tiles, kNumSMs) / CL * CL;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(128 + GROUPS * 128);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  L2I_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tw, p));
   return check_launch("conv_tc_ares");
 }
 
@@ -325,7 +352,8 @@ int launch_conv_tc_ares(const void* in, const __nv_bfloat16* w, const ConvGeom& 
   {
     const uint64_t dims[3] = {(uint64_t)g.Cin, (uint64_t)g.Cout, 9};
     const uint64_t str[3] = {2, (uint64_t)g.Cin * 2, (uint64_t)g.Cout * g.Cin * 2};
-    const uint32_t box[3] = {64, (uint32_t)g.Cout, 1};
+    const bool pair_w = !comp && g_switches.cluster && (int64_t)ceil_div(g.W, kRTileW) * ceil_div(g.H, kRTileH) * g.B >= 2;
+    const uint32_t box[3] = {64, (uint32_t)(pair_w ? g.Cout / 2 : g.Cout), 1};   // a CTA of a pair loads half of the tile's rows
     L2I_TRY(make_tmap(&tw, w, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
   }
   p.tiles_x = ceil_div(g.W, kRTileW); p.tiles_y = ceil_div(g.H, kRTileH);
@@ -333,8 +361,10 @@ int launch_conv_tc_ares(const void* in, const __nv_bfloat16* w, const ConvGeom& 
   if (total <= 0 || total > 0x7fffffff) { set_error("conv_tc_ares: bad tile count"); return L2I_ERR_INVALID_ARG; }
   p.total_tiles = (int)total;
   // ring depth: the weight tiles in flight must cover the L2 latency (~1.5-2k clocks): 7 x 256 / 4 x 512 MMA clocks
-  if (comp) return launch_ares_variant<256, 2, 1, 4, 2, EPI_ACT, true>(ta, tw, p, st);
-  return launch_ares_variant<128, 2, 2, 3, 2, EPI_ACT_RGB, false>(ta, tw, p, st);
+  const bool pair = g_switches.cluster && p.total_tiles >= 2;
+  if (comp) return launch_ares_variant<256, 2, 1, 4, 2, EPI_ACT, true, 1>(ta, tw, p, st);
+  if (pair) return launch_ares_variant<128, 2, 2, 3, 2, EPI_ACT_RGB, false, 2>(ta, tw, p, st);
+  return launch_ares_variant<128, 2, 2, 3, 2, EPI_ACT_RGB, false, 1>(ta, tw, p, st);
 }
 
 }  // namespace l2i
