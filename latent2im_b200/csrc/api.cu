@@ -32,7 +32,8 @@ void refresh_kernel_switches() {
   s.fir_simt = flag("L2I_FIR_SIMT", 0) != 0;
   s.uprow = flag("L2I_UPROW", 1) != 0;
   s.uprow_mask = flag("L2I_UPROW_MASK", 7);
-  s.cluster = flag("L2I_CLUSTER", 1);
+  s.cluster = flag("L2I_CLUSTER", 0);
+  s.ares_pair = flag("L2I_ARES_PAIR", 1) != 0;
   g_switches = s;
 }
 

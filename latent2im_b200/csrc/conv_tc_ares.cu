@@ -8,6 +8,8 @@
 // the nine taps are UMMA descriptors at tap-shifted start addresses (as in conv_tc_halo.cu); only the weight tiles
 // stream through a shared-memory ring, fed by their own producer warp.  L2 -> SMEM bytes per tile: 46 KB + 9 x 2 x B-tile
 // instead of 9 x 2 x (16 KB + B-tile).
+#include <type_traits>
+
 #include "tc_epilogue.cuh"
 
 namespace l2i {
@@ -47,12 +49,7 @@ __device__ __forceinline__ void ares_group_sync(int group) {
 // N = GEMM N, KC = 64-channel chunks of Cin, BP = chunks per weight-ring stage (1 or KC), WST = weight ring stages,
 // COMP = composite up-conv (N = 4 phases x N/4).  The single MMA-issuing thread pays ~100 clocks of mbarrier latency per
 // ring stage; with N = 128 a 64-channel stage is only 256 tensor clocks, so those layers take whole taps (BP = KC) per stage.
-// CL = CTAs per cluster (1 or 2).  The weight-tile sequence is the same for every output tile, so the CTAs of a cluster run their
-// weight rings in lockstep: each loads 1 / CL of every stage and TMA-multicasts it to all of them, and a stage is free again when the
-// MMAs of every CTA have read it (multicast commit).  Why: at batch 32 the 128 -> 128 layer streams 9 x 32 KB of weights per
-// 128-pixel tile = 4.7 GB per launch from L2, which alone takes the 0.58 ms the layer measured (~8 TB/s); pairs halve it.
-// Every CTA runs the same number of tiles (indices past the end: zero-filled loads, masked epilogue), or the rings would deadlock.
-template <int N, int KC, int BP, int WST, int GROUPS, int EPI, bool COMP, int CL>
+template <int N, int KC, int BP, int WST, int GROUPS, int EPI, bool COMP>
 __global__ void __launch_bounds__(128 + GROUPS * 128, 1)
 conv_tc_ares_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ AresParams p) {
@@ -84,20 +81,15 @@ conv_tc_ares_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kRAStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < WST; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], CL); }
+    for (int s = 0; s < WST; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int a = 0; a < GROUPS; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();      // the peers' barriers are initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
-  constexpr uint16_t kClusterMask = (uint16_t)((1u << CL) - 1u);
-  // same trip count in every CTA; a tile index past the end decodes to sample b >= B (loads zero-filled, nothing stored)
-  const int tile_end = CL > 1 ? (int)blockIdx.x + (int)gridDim.x * ((p.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x) : p.total_tiles;
 
   auto decode = [&](int tile, int& x0, int& y0, int& b) {
     const int tx = tile % p.tiles_x;
@@ -112,7 +104,7 @@ conv_tc_ares_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase_bit = 0;
-      for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int x0, y0, b;
         decode(tile, x0, y0, b);
         mbar_wait(&a_empty[stage], phase_bit ^ 1);
@@ -128,20 +120,15 @@ conv_tc_ares_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (lane == 0) {
       int ws = 0;
       uint32_t wphase = 0;
-      for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         for (int t = 0; t < 9; ++t) {
 #pragma unroll
           for (int kc = 0; kc < KC; kc += BP) {
             mbar_wait(&w_empty[ws], wphase ^ 1);
             mbar_expect_tx(&w_full[ws], kBStageBytes);
 #pragma unroll
-            for (int j = 0; j < BP; ++j) {
-              if (CL > 1)   // this CTA's N / CL rows of the tile, to every CTA of the cluster
-                tma_load_3d_mc(smem_b + ws * kBStageBytes + j * kBPlaneBytes + cta_rank * (N / CL) * 128, &tmap_w, &w_full[ws], (kc + j) * 64,
-                               (int)cta_rank * (N / CL), t, kClusterMask);
-              else
-                tma_load_3d(smem_b + ws * kBStageBytes + j * kBPlaneBytes, &tmap_w, &w_full[ws], (kc + j) * 64, 0, t);
-            }
+            for (int j = 0; j < BP; ++j)
+              tma_load_3d(smem_b + ws * kBStageBytes + j * kBPlaneBytes, &tmap_w, &w_full[ws], (kc + j) * 64, 0, t);
             if (++ws == WST) { ws = 0; wphase ^= 1; }
           }
         }
@@ -155,7 +142,7 @@ conv_tc_ares_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t smem_a0 = smem_u32(smem), smem_b0 = smem_u32(smem_b);
       constexpr uint64_t kHiA = kmajor_desc_hi(kRW * 128, 2), kHiB = kmajor_desc_hi(1024, 2);
-      for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty[grp], grp_phase ^ 1);
         mbar_wait(&a_full[stage], phase_bit);
         tc_fence_after();
@@ -178,8 +165,7 @@ conv_tc_ares_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                   umma_bf16(tmem_d, a_desc + (uint64_t)((j * kRPlaneStride + k * 32) >> 4), b_desc + (uint64_t)((j * kBPlaneBytes + k * 32) >> 4),
                             p.idesc, (t | kc | j | k) != 0 ? 1u : 0u);
               }
-              if (CL > 1) umma_commit_mc(&w_empty[ws], kClusterMask);
-              else umma_commit(&w_empty[ws]);
+              umma_commit(&w_empty[ws]);
             }
             if (++ws == WST) { ws = 0; wphase ^= 1; }
           }
@@ -211,14 +197,14 @@ conv_tc_ares_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint32_t grp_phase = 0;
     int staged_b = -1;
     int it = 0;
-    for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       if (it % GROUPS != group) continue;
       int x0, y0, b;
       decode(tile, x0, y0, b);
       const int ox = x0 + lx, oy = y0 + ly;
-      const bool ok = ox < p.W && oy < p.H && b < p.B;
+      const bool ok = ox < p.W && oy < p.H;
 
-      if (b != staged_b && b < p.B) {
+      if (b != staged_b) {
         ares_group_sync(group);
         for (int j = gtid; j < CO; j += 128) {
           s_d[j] = (e.demod != nullptr ? __ldg(e.demod + (int64_t)b * e.demod_bs + j) : 1.f) * kSqrt2;
@@ -293,35 +279,329 @@ conv_tc_ares_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();      // no CTA leaves while a peer may still multicast into it or arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
 }
 
-template <int N, int KC, int BP, int WST, int GROUPS, int EPI, bool COMP, int CL>
-int launch_ares_variant(const CUtensorMap& ta, const CUtensorMap& tw, const AresParams& p, cudaStream_t st) {
-  constexpr int smem = kRAStages * KC * kRPlaneStride + WST * BP * N * 128 + 1024;
-  static_assert(smem + GROUPS * 6 * (COMP ? N / 4 : N) * 4 + 512 <= 227 * 1024, "shared memory budget (dynamic + static epilogue vectors)");
-  auto kern = conv_tc_ares_kernel<N, KC, BP, WST, GROUPS, EPI, COMP, CL>;
+// ---------------------------------------------------------------------------------------------------------------------------
+// Plain 128 -> 128 layer (act + ToRGB epilogue), round 2: TILE PAIRS.  The epilogue of the kernel above owns one pixel x 128
+// channels per lane and fetches six per-channel vectors for it with warp-wide LDS.128 (four shared-memory wavefronts each, same
+// address or not), then writes its 256 bytes with 16-byte stores at pixel pitch (one wavefront per lane): 3072 + 2048 wavefronts per
+// tile next to the 4608 of the MMA operands and the 2664 of the TMA fills - the shared-memory / L1 data pipe bounds the layer
+// (ncu: tensor pipe 57 %).  Here a CTA walks a CONTIGUOUS tile range, four accumulators live in TMEM, an epilogue warpgroup
+// takes two consecutive tiles at once so that every vector fetched serves two pixels (epilogue_pair16), and the activation leaves
+// through per-warp staging tiles and TMA tensor stores.
+constexpr int kR2Accs = 4;
+constexpr int kR2StageOut = 2048;      // per epilogue warp: [tile of the pair][32 pixels][16 channels] bf16
+
+template <int WST>
+__global__ void __launch_bounds__(128 + 2 * 128, 1)
+conv_tc_ares_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                         const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ AresParams p) {
+  constexpr int N = 128, KC = 2, CO = 128;
+  constexpr int kAStageBytes = KC * kRPlaneStride;
+  constexpr int kBPlaneBytes = N * 128;
+  constexpr int kBStageBytes = KC * kBPlaneBytes;      // one tap (both 64-channel planes) per ring stage
+  constexpr int kEpiFloats = 6 * CO;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem_b = smem + kRAStages * kAStageBytes;
+  uint8_t* smem_out = smem_b + WST * kBStageBytes;
+  __shared__ __align__(16) float epi_smem[2 * kEpiFloats];
+  __shared__ __align__(8) uint64_t a_full[kRAStages];
+  __shared__ __align__(8) uint64_t a_empty[kRAStages];
+  __shared__ __align__(8) uint64_t w_full[WST];
+  __shared__ __align__(8) uint64_t w_empty[WST];
+  __shared__ __align__(8) uint64_t tmem_full[kR2Accs];
+  __shared__ __align__(8) uint64_t tmem_empty[kR2Accs];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_w);
+    prefetch_tmap(&tmap_o);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kRAStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < WST; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int a = 0; a < kR2Accs; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  // contiguous tile range of this CTA: neighbouring tiles share halo rows in L2 and, almost always, the sample
+  const int t_begin = (int)((int64_t)p.total_tiles * blockIdx.x / gridDim.x);
+  const int t_end = (int)((int64_t)p.total_tiles * (blockIdx.x + 1) / gridDim.x);
+  auto decode = [&](int tile, int& x0, int& y0, int& b) {
+    const int tx = tile % p.tiles_x;
+    const int r = tile / p.tiles_x;
+    const int ty = r % p.tiles_y;
+    b = r / p.tiles_y;
+    x0 = tx * kRTileW; y0 = ty * kRTileH;
+  };
+
+  if (warp == 0) {
+    // ===================== A producer: the halo tile (KC planes) once per output tile =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase_bit = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        int x0, y0, b;
+        decode(tile, x0, y0, b);
+        mbar_wait(&a_empty[stage], phase_bit ^ 1);
+        mbar_expect_tx(&a_full[stage], KC * kRPlaneBytes);
+#pragma unroll
+        for (int kc = 0; kc < KC; ++kc)
+          tma_load_4d(smem + stage * kAStageBytes + kc * kRPlaneStride, &tmap_a, &a_full[stage], kc * 64, x0 - 1, y0 - 1, b);
+        if (++stage == kRAStages) { stage = 0; phase_bit ^= 1; }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== B producer: 9 taps per output tile through the ring =====================
+    if (lane == 0) {
+      int ws = 0;
+      uint32_t wphase = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        for (int t = 0; t < 9; ++t) {
+          mbar_wait(&w_empty[ws], wphase ^ 1);
+          mbar_expect_tx(&w_full[ws], kBStageBytes);
+#pragma unroll
+          for (int j = 0; j < KC; ++j) tma_load_3d(smem_b + ws * kBStageBytes + j * kBPlaneBytes, &tmap_w, &w_full[ws], j * 64, 0, t);
+          if (++ws == WST) { ws = 0; wphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: warp-uniform control flow, one elected lane issues (tc_ptx.cuh: elect_one) =============
+    int stage = 0, ws = 0;
+    uint32_t phase_bit = 0, wphase = 0;
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t smem_a0 = smem_u32(smem), smem_b0 = smem_u32(smem_b);
+    constexpr uint64_t kHiA = kmajor_desc_hi(kRW * 128, 2), kHiB = kmajor_desc_hi(1024, 2);
+    int it = 0;
+    for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+      const int acc = it & (kR2Accs - 1);
+      mbar_wait(&tmem_empty[acc], (((uint32_t)it / kR2Accs) & 1u) ^ 1u);
+      mbar_wait(&a_full[stage], phase_bit);
+      tc_fence_after();
+      const uint32_t a_base = smem_a0 + (uint32_t)(stage * kAStageBytes);
+      const uint32_t tmem_d = tmem_u + (uint32_t)(acc * N);
+#pragma unroll 1
+      for (int t = 0; t < 9; ++t) {
+        const uint32_t shift = (uint32_t)(((t / 3) * kRW + (t % 3)) * 128);   // tap (dy, dx) = (t/3 - 1, t%3 - 1)
+        mbar_wait(&w_full[ws], wphase);
+        tc_fence_after();
+        const uint64_t a_desc = kmajor_desc_at(kHiA, a_base + shift);
+        const uint64_t b_desc = kmajor_desc_at(kHiB, smem_b0 + (uint32_t)(ws * kBStageBytes));
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < KC; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_d, a_desc + (uint64_t)((j * kRPlaneStride + k * 32) >> 4), b_desc + (uint64_t)((j * kBPlaneBytes + k * 32) >> 4),
+                        p.idesc, (t | j | k) != 0 ? 1u : 0u);
+          umma_commit(&w_empty[ws]);
+        }
+        if (++ws == WST) { ws = 0; wphase ^= 1; }
+      }
+      if (elect_one()) {
+        umma_commit(&a_empty[stage]);
+        umma_commit(&tmem_full[acc]);
+      }
+      if (++stage == kRAStages) { stage = 0; phase_bit ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: warpgroup g takes the tile pairs (4k + 2g, 4k + 2g + 1) = accumulators 2g, 2g + 1 ==========
+    const EpiParams& e = p.e;
+    const int group = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int gtid = threadIdx.x - (128 + group * 128);
+    float* sp = epi_smem + group * kEpiFloats;
+    float* s_d = sp;
+    float* s_b = sp + CO;
+    float* s_n = sp + 2 * CO;
+    float* s_w = sp + 3 * CO;
+    constexpr float kSqrt2 = 1.4142135623730951f;
+    const float nw = (e.noise != nullptr && e.noise_w != nullptr) ? __ldg(e.noise_w) * kSqrt2 : 0.f;
+    const int64_t plane = (int64_t)p.out_H * p.out_W;
+    const int lx = row & 7, ly = row >> 3;
+    uint8_t* stage_tile = smem_out + (warp - 4) * kR2StageOut;
+    uint4* stage_row = reinterpret_cast<uint4*>(stage_tile + lane * 32);
+    const int stage_swp = (lane >> 2) & 1;                 // bank-conflict-free order of the two 16-byte halves of a 32-byte row
+    const bool want_out = e.out != nullptr && e.s_next != nullptr;
+    int staged_b = -1;
+    const int ntiles = t_end - t_begin;
+    for (int it0 = 2 * group; it0 < ntiles; it0 += 4) {
+      const uint32_t acc_parity = ((uint32_t)it0 / kR2Accs) & 1u;
+      const bool have2 = it0 + 1 < ntiles;
+      int x0[2], y0[2], bb[2];
+      decode(t_begin + it0, x0[0], y0[0], bb[0]);
+      if (have2) decode(t_begin + it0 + 1, x0[1], y0[1], bb[1]);
+      else { x0[1] = x0[0]; y0[1] = y0[0]; bb[1] = bb[0]; }
+      // ---- global loads of both tiles before waiting for the accumulators ----
+      float nz[2] = {0.f, 0.f}, up[2][3];
+      bool ok[2];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int ox = x0[s] + lx, oy = y0[s] + ly;
+        ok[s] = ox < p.W && oy < p.H && (s == 0 || have2);
+        if (ok[s] && e.noise != nullptr) nz[s] = nw * __ldg(e.noise + (int64_t)bb[s] * e.noise_bs + (int64_t)oy * p.out_W + ox);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          up[s][c] = 0.f;
+          if (ok[s] && e.fused_skip) {
+            up[s][c] = __ldg(e.rgb_bias + c);
+            if (e.skip_in != nullptr)
+              up[s][c] += upsample2x_at(e.skip_in + ((int64_t)bb[s] * 3 + c) * (plane / 4), p.out_H / 2, p.out_W / 2, oy, ox, e.fir);
+          }
+        }
+      }
+      mbar_wait(&tmem_full[2 * group], acc_parity);
+      if (have2) mbar_wait(&tmem_full[2 * group + 1], acc_parity);
+      tc_fence_after();
+      // a pair that straddles two samples (once per CTA at most, the tile range is contiguous) is processed one tile at a time
+      uint64_t rgb2[2][3] = {{0ull, 0ull, 0ull}, {0ull, 0ull, 0ull}};
+      // MODE 0: both tiles at once; MODE 1 / 2: tile 0 / tile 1 alone (compile-time indices keep rgb2 & co. in registers)
+      auto run_pass = [&](auto mode_c) {
+        constexpr int MODE = decltype(mode_c)::value;
+        constexpr int sa = MODE == 2 ? 1 : 0, sb = MODE == 0 ? 1 : sa;   // accumulators feeding "pixel a" / "pixel b"
+        constexpr bool two = MODE == 0;
+        uint64_t rgb_unused[3] = {0ull, 0ull, 0ull};
+        const int b = bb[sa];
+        if (b != staged_b) {
+          ares_group_sync(group);
+          for (int j = gtid; j < CO; j += 128) {
+            s_d[j] = (e.demod != nullptr ? __ldg(e.demod + (int64_t)b * e.demod_bs + j) : 1.f) * kSqrt2;
+            s_b[j] = __ldg(e.bias + j) * kSqrt2;
+            s_n[j] = e.s_next ? __ldg(e.s_next + (int64_t)b * e.s_next_bs + j) : 1.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) s_w[c * CO + j] = e.wr ? __ldg(e.wr + (int64_t)b * e.wr_bs + c * p.Cout + j) : 0.f;
+          }
+          ares_group_sync(group);
+          staged_b = b;
+        }
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((2 * group + sa) * N);
+        const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((2 * group + sb) * N);
+        const int64_t pixa = ((int64_t)bb[sa] * p.out_H + y0[sa] + ly) * p.out_W + x0[sa] + lx;
+        const int64_t pixb = ((int64_t)bb[sb] * p.out_H + y0[sb] + ly) * p.out_W + x0[sb] + lx;
+#pragma unroll 1
+        for (int cs = 0; cs < N; cs += 16) {
+          uint32_t va[16], vb[16];
+          tmem_ld16(ta + cs, va);
+          tmem_ld16(tb + cs, vb);
+          tmem_ld_wait();
+          uint32_t oa[8], ob[8], ya[8], yb[8];
+          if (e.y_out != nullptr)
+            epilogue_pair16<true, true>(va, vb, s_d + cs, s_b + cs, s_n + cs, s_w + cs, s_w + CO + cs, s_w + 2 * CO + cs, nz[sa], nz[sb],
+                                        rgb2[sa], two ? rgb2[sb] : rgb_unused, oa, ob, ya, yb);
+          else
+            epilogue_pair16<true, false>(va, vb, s_d + cs, s_b + cs, s_n + cs, s_w + cs, s_w + CO + cs, s_w + 2 * CO + cs, nz[sa], nz[sb],
+                                         rgb2[sa], two ? rgb2[sb] : rgb_unused, oa, ob, ya, yb);
+          if (e.y_out != nullptr) {   // training: the unscaled activation is kept for the backward pass
+            if (ok[sa]) {
+              uint4* yd = reinterpret_cast<uint4*>((__nv_bfloat16*)e.y_out + pixa * CO + cs);
+              yd[0] = make_uint4(ya[0], ya[1], ya[2], ya[3]);
+              yd[1] = make_uint4(ya[4], ya[5], ya[6], ya[7]);
+            }
+            if (two && ok[sb]) {
+              uint4* yd = reinterpret_cast<uint4*>((__nv_bfloat16*)e.y_out + pixb * CO + cs);
+              yd[0] = make_uint4(yb[0], yb[1], yb[2], yb[3]);
+              yd[1] = make_uint4(yb[4], yb[5], yb[6], yb[7]);
+            }
+          }
+          if (want_out) {
+            if (lane == 0) tma_store_wait_read();       // the previous stores have finished reading this warp's staging tiles
+            __syncwarp();
+            const uint4 a_lo = make_uint4(oa[0], oa[1], oa[2], oa[3]), a_hi = make_uint4(oa[4], oa[5], oa[6], oa[7]);
+            stage_row[stage_swp] = stage_swp ? a_hi : a_lo;
+            stage_row[stage_swp ^ 1] = stage_swp ? a_lo : a_hi;
+            if (two) {
+              const uint4 b_lo = make_uint4(ob[0], ob[1], ob[2], ob[3]), b_hi = make_uint4(ob[4], ob[5], ob[6], ob[7]);
+              stage_row[64 + stage_swp] = stage_swp ? b_hi : b_lo;
+              stage_row[64 + (stage_swp ^ 1)] = stage_swp ? b_lo : b_hi;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {      // a warp's 8 columns x 4 rows of a tile; the tensor map clips what lies outside the image
+              if (two) tma_store_4d_nocommit(&tmap_o, stage_tile + 1024, cs, x0[sb], y0[sb] + 4 * q, bb[sb]);
+              tma_store_4d(&tmap_o, stage_tile, cs, x0[sa], y0[sa] + 4 * q, bb[sa]);
+            }
+          }
+        }
+      };
+      if (!have2) {
+        run_pass(std::integral_constant<int, 1>{});
+      } else if (bb[1] != bb[0]) {
+        run_pass(std::integral_constant<int, 1>{});
+        run_pass(std::integral_constant<int, 2>{});
+      } else {
+        run_pass(std::integral_constant<int, 0>{});
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[2 * group]);
+      if (have2) mbar_arrive(&tmem_empty[2 * group + 1]);
+
+      if (e.wr != nullptr) {
+        float* dst = e.fused_skip ? e.skip_out : e.rgb_part;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (!ok[s]) continue;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float lo, hi;
+            upk2(rgb2[s][c], lo, hi);
+            dst[((int64_t)bb[s] * 3 + c) * plane + (int64_t)(y0[s] + ly) * p.out_W + x0[s] + lx] = (lo + hi) + up[s][c];
+          }
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int WST>
+int launch_ares_pair(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const AresParams& p, cudaStream_t st) {
+  constexpr int smem = kRAStages * 2 * kRPlaneStride + WST * 2 * 128 * 128 + 8 * kR2StageOut + 1024;
+  static_assert(smem + 2 * 6 * 128 * 4 + 512 <= 227 * 1024, "shared memory budget (dynamic + static epilogue vectors)");
+  auto kern = conv_tc_ares_pair_kernel<WST>;
   static bool attr_set = false;
   if (!attr_set) {
     L2I_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  const int grid = std::min(p.total_tiles, kNumSMs) / CL * CL;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(128 + GROUPS * 128);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  L2I_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tw, p));
+  const int grid = std::min(p.total_tiles, kNumSMs);
+  kern<<<grid, 128 + 2 * 128, smem, st>>>(ta, tw, to, p);
+  return check_launch("conv_tc_ares_pair");
+}
+
+template <int N, int KC, int BP, int WST, int GROUPS, int EPI, bool COMP>
+int launch_ares_variant(const CUtensorMap& ta, const CUtensorMap& tw, const AresParams& p, cudaStream_t st) {
+  constexpr int smem = kRAStages * KC * kRPlaneStride + WST * BP * N * 128 + 1024;
+  static_assert(smem + GROUPS * 6 * (COMP ? N / 4 : N) * 4 + 512 <= 227 * 1024, "shared memory budget (dynamic + static epilogue vectors)");
+  auto kern = conv_tc_ares_kernel<N, KC, BP, WST, GROUPS, EPI, COMP>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    L2I_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int grid = std::min(p.total_tiles, kNumSMs);
+  kern<<<grid, 128 + GROUPS * 128, smem, st>>>(ta, tw, p);
   return check_launch("conv_tc_ares");
 }
 
@@ -352,8 +632,7 @@ int launch_conv_tc_ares(const void* in, const __nv_bfloat16* w, const ConvGeom& 
   {
     const uint64_t dims[3] = {(uint64_t)g.Cin, (uint64_t)g.Cout, 9};
     const uint64_t str[3] = {2, (uint64_t)g.Cin * 2, (uint64_t)g.Cout * g.Cin * 2};
-    const bool pair_w = !comp && g_switches.cluster && (int64_t)ceil_div(g.W, kRTileW) * ceil_div(g.H, kRTileH) * g.B >= 2;
-    const uint32_t box[3] = {64, (uint32_t)(pair_w ? g.Cout / 2 : g.Cout), 1};   // a CTA of a pair loads half of the tile's rows
+    const uint32_t box[3] = {64, (uint32_t)g.Cout, 1};
     L2I_TRY(make_tmap(&tw, w, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
   }
   p.tiles_x = ceil_div(g.W, kRTileW); p.tiles_y = ceil_div(g.H, kRTileH);
@@ -361,10 +640,19 @@ int launch_conv_tc_ares(const void* in, const __nv_bfloat16* w, const ConvGeom& 
   if (total <= 0 || total > 0x7fffffff) { set_error("conv_tc_ares: bad tile count"); return L2I_ERR_INVALID_ARG; }
   p.total_tiles = (int)total;
   // ring depth: the weight tiles in flight must cover the L2 latency (~1.5-2k clocks): 7 x 256 / 4 x 512 MMA clocks
-  const bool pair = g_switches.cluster && p.total_tiles >= 2;
-  if (comp) return launch_ares_variant<256, 2, 1, 4, 2, EPI_ACT, true, 1>(ta, tw, p, st);
-  if (pair) return launch_ares_variant<128, 2, 2, 3, 2, EPI_ACT_RGB, false, 2>(ta, tw, p, st);
-  return launch_ares_variant<128, 2, 2, 3, 2, EPI_ACT_RGB, false, 1>(ta, tw, p, st);
+  if (comp) return launch_ares_variant<256, 2, 1, 4, 2, EPI_ACT, true>(ta, tw, p, st);
+  if (g_switches.ares_pair && (e.out == nullptr || (uintptr_t)e.out % 16 == 0)) {
+    CUtensorMap to = ta;   // placeholder when the layer has no activation output
+    if (e.out != nullptr && e.s_next != nullptr) {
+      // a warp's 32 pixels of a tile: 8 columns x 4 rows, 16 of the 128 channels per store
+      const uint64_t dims[4] = {(uint64_t)g.Cout, (uint64_t)g.out_W, (uint64_t)g.out_H, (uint64_t)g.B};
+      const uint64_t str[4] = {2, (uint64_t)g.Cout * 2, (uint64_t)g.out_W * g.Cout * 2, (uint64_t)g.out_H * g.out_W * g.Cout * 2};
+      const uint32_t box[4] = {16, 8, 4, 1};
+      L2I_TRY(make_tmap(&to, e.out, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE));
+    }
+    return launch_ares_pair<3>(ta, tw, to, p, st);
+  }
+  return launch_ares_variant<128, 2, 2, 3, 2, EPI_ACT_RGB, false>(ta, tw, p, st);
 }
 
 }  // namespace l2i

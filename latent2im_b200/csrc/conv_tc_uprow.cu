@@ -56,7 +56,8 @@ struct UprowParams {
   int B, H, W;                 // input grid
   int Cout;                    // all output channels of the layer (pixel pitch of the output tensor)
   int nch, nseg;               // channel parts (Cout / CO), column segments (W / 128)
-  int64_t total_rows;          // B * nch * nseg * H
+  int64_t total_rows;          // B * nch * nseg * H (CTA pairs: B / 2 samples per CTA of a pair)
+  int b_pair_off;              // CTA pairs: rank 1 works on sample b + b_pair_off of the same (channel part, segment, row) range
   EpiParams e;
 };
 
@@ -74,7 +75,7 @@ struct Run {
 };
 
 // the r-th flattened row -> (sample, channel part, segment, input row); the run ends at the unit's last row or at r_end
-__device__ __forceinline__ Run decode_run(const UprowParams& p, int64_t r, int64_t r_end) {
+__device__ __forceinline__ Run decode_run(const UprowParams& p, int64_t r, int64_t r_end, int b_off = 0) {
   Run q;
   const int64_t unit = r / p.H;
   q.m0 = (int)(r - unit * p.H);
@@ -82,14 +83,18 @@ __device__ __forceinline__ Run decode_run(const UprowParams& p, int64_t r, int64
   q.seg = (int)(unit % p.nseg);
   const int64_t t = unit / p.nseg;
   q.ch = (int)(t % p.nch);
-  q.b = (int)(t / p.nch);
+  q.b = (int)(t / p.nch) + b_off;
   return q;
 }
 
 // CO = output channels per work unit (GEMM N = 2 * CO), KC = Cin / 64, AS = input-row ring slots,
 // BRES = weights resident (all 9 * KC planes), else streamed: BP planes of one (kh, dx) tile per stage, WST stages.
 // Eight epilogue warps: (TMEM lane quadrant) x (half of the CO channels); see the epilogue for the lane -> pixel / channel map.
-template <int CO, int KC, int AS, bool BRES, int BP, int WST, int EW>
+// CL = 2 (streamed weights only): CTA pairs.  Both CTAs of a cluster walk the SAME (channel part, segment, row) range of two
+// different samples, so their weight rings run in lockstep: each loads half of every stage's rows and TMA-multicasts it to both,
+// and a stage is free when the MMAs of both have read it (multicast commit).  The 256 -> 128 layer streams 576 KB of weights per
+// input row from L2 (4.7 GB per launch at batch 32), its MMA issuer waited for weights a third of the time.
+template <int CO, int KC, int AS, bool BRES, int BP, int WST, int EW, int CL>
 __global__ void __launch_bounds__(128 + EW * 32, 1)
 conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                      const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ UprowParams p) {
@@ -139,7 +144,7 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < AS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < (BRES ? 1 : WST); ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int s = 0; s < (BRES ? 1 : WST); ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], CL); }
     for (int s = 0; s < kSlots; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiWarps); }
     for (int s = 0; s < kNoiseSlots; ++s) { mbar_init(&n_full[s], 1); mbar_init(&n_empty[s], kEpiWarps); }
     fence_barrier_init();
@@ -147,11 +152,16 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();      // the peer's barriers are initialised before anything is multicast to it
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
-  const int64_t r_begin = p.total_rows * (int64_t)blockIdx.x / gridDim.x;
-  const int64_t r_end = p.total_rows * (int64_t)(blockIdx.x + 1) / gridDim.x;
+  static_assert(CL == 1 || (CL == 2 && !BRES), "CTA pairs share the streamed weight ring");
+  const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t kClusterMask = (uint16_t)((1u << CL) - 1u);
+  const int b_off = (int)cta_rank * p.b_pair_off;
+  const int64_t r_begin = p.total_rows * (int64_t)(blockIdx.x / CL) / (gridDim.x / CL);
+  const int64_t r_end = p.total_rows * (int64_t)(blockIdx.x / CL + 1) / (gridDim.x / CL);
 
   // register budget: the producer / MMA warpgroup needs few, the 8 epilogue warps hold the FIR state of up to 64 channels.
   // setmaxnreg.inc can only take what .dec released inside THIS CTA's launch allocation (384 threads x 168 registers): a
@@ -172,7 +182,7 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       }
       uint32_t acnt = 0;
       for (int64_t r = r_begin; r < r_end;) {
-        const Run q = decode_run(p, r, r_end);
+        const Run q = decode_run(p, r, r_end, b_off);
         for (int row = q.m0 - 1; row <= q.m0 + q.R; ++row, ++acnt) {
           const int slot = acnt % AS;
           mbar_wait_sleep(&a_empty[slot], ((acnt / AS) & 1) ^ 1);
@@ -189,7 +199,7 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     if (!BRES && lane == 0) {
       uint32_t wcnt = 0;
       for (int64_t r = r_begin; r < r_end;) {
-        const Run q = decode_run(p, r, r_end);
+        const Run q = decode_run(p, r, r_end, b_off);
         const int nrows = 2 * q.R + 3;
         for (int k = 0; k < nrows; ++k) {
           const int py = (k & 1) ^ 1;                       // u = 2 m0 - 1 + k
@@ -202,9 +212,14 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 mbar_wait_sleep(&w_empty[ws], ((wcnt / WST) & 1) ^ 1);
                 mbar_expect_tx(&w_full[ws], kBStageBytes);
 #pragma unroll
-                for (int j = 0; j < BP; ++j)
-                  tma_load_3d(smem_b + ws * kBStageBytes + j * kBPlaneBytes, &tmap_w, &w_full[ws], (kc + j) * 64, 0,
-                              q.ch * 9 + kh * 3 + dxi);
+                for (int j = 0; j < BP; ++j) {
+                  if (CL > 1)   // this CTA's half of the tile's rows, to both CTAs of the pair
+                    tma_load_3d_mc(smem_b + ws * kBStageBytes + j * kBPlaneBytes + cta_rank * (N / CL) * 128, &tmap_w, &w_full[ws],
+                                   (kc + j) * 64, (int)cta_rank * (N / CL), q.ch * 9 + kh * 3 + dxi, kClusterMask);
+                  else
+                    tma_load_3d(smem_b + ws * kBStageBytes + j * kBPlaneBytes, &tmap_w, &w_full[ws], (kc + j) * 64, 0,
+                                q.ch * 9 + kh * 3 + dxi);
+                }
               }
             }
           }
@@ -218,7 +233,7 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     if (lane == 0 && p.e.noise != nullptr) {
       uint32_t ncnt = 0;
       for (int64_t r = r_begin; r < r_end;) {
-        const Run q = decode_run(p, r, r_end);
+        const Run q = decode_run(p, r, r_end, b_off);
         const float* src = p.e.noise + (int64_t)q.b * p.e.noise_bs + (int64_t)(2 * q.m0) * (2 * p.W) + 2 * q.seg * kSegW;
         for (int j = 0; j < 2 * q.R; ++j, ++ncnt) {
           const int slot = ncnt % kNoiseSlots;
@@ -295,7 +310,8 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                   umma_bf16(tmem_d, a_desc + (uint64_t)(((kc + j) * kPlaneStride + dxi * 128 + kk * 32) >> 4),
                             b_desc + (uint64_t)((j * kBPlaneBytes + kk * 32) >> 4), kIdesc,
                             (first == 0 && dxi == 0 && kc == 0 && j == 0 && kk == 0) ? 0u : 1u);
-              umma_commit(&w_empty[ws]);
+              if (CL > 1) umma_commit_mc(&w_empty[ws], kClusterMask);
+              else umma_commit(&w_empty[ws]);
             }
             ++wcnt;
           }
@@ -304,7 +320,7 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       if (BRES) {
         static_assert(!BRES || (KC == 1 && kSlots % 2 == 0), "paired MMAs: one weight plane per tile, slot pairs");
         for (int64_t r = r_begin; r < r_end;) {
-          const Run q = decode_run(p, r, r_end);
+          const Run q = decode_run(p, r, r_end, b_off);
           // a run's first Hb row (u = 2 m0 - 1, kh 1 alone) takes an ODD slot so that every later pair (u = 2m, 2m+1) is an aligned
           // slot pair; an even start first hands an empty slot through (the epilogue does the same)
           if (!(tcnt & 1)) {
@@ -353,7 +369,7 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         }
       } else
       for (int64_t r = r_begin; r < r_end;) {
-        const Run q = decode_run(p, r, r_end);
+        const Run q = decode_run(p, r, r_end, b_off);
         const int nrows = 2 * q.R + 3;
         for (int k = 0; k < nrows; ++k, ++tcnt) {
           const int ml = (k + 1) >> 1;                      // ring-local index of input row m = floor(u / 2): m - (m0 - 1)
@@ -424,7 +440,7 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     uint64_t st[NPART][NCHK][2][8];
     uint64_t rD[PREG ? 8 : 1], rB[PREG ? 8 : 1], rN[PREG ? 8 : 1];
     for (int64_t r = r_begin; r < r_end;) {
-      const Run q = decode_run(p, r, r_end);
+      const Run q = decode_run(p, r, r_end, b_off);
       const int nrows = 2 * q.R + 3;
       // per-(sample, channel part) epilogue vectors
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
@@ -627,25 +643,36 @@ conv_tc_uprow_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();      // no CTA leaves while its peer may still multicast into it or arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
 }
 
-template <int CO, int KC, int AS, bool BRES, int BP, int WST, int EW>
+template <int CO, int KC, int AS, bool BRES, int BP, int WST, int EW, int CL>
 int launch_uprow_variant(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const UprowParams& p, cudaStream_t st) {
   constexpr int N = 2 * CO;
   constexpr int smem = AS * KC * kPlaneStride + (BRES ? 9 * KC : WST * BP) * N * 128 + EW * 2048 + 1024;
   static_assert(smem + 3 * CO * 4 + kNoiseSlots * 1024 + 512 <= 227 * 1024, "shared memory budget (dynamic + static)");
-  auto kern = conv_tc_uprow_kernel<CO, KC, AS, BRES, BP, WST, EW>;
+  auto kern = conv_tc_uprow_kernel<CO, KC, AS, BRES, BP, WST, EW, CL>;
   static bool attr_set = false;
   if (!attr_set) {
     L2I_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  const int grid = (int)std::min<int64_t>(p.total_rows, kNumSMs);
-  kern<<<grid, 128 + EW * 32, smem, st>>>(ta, tw, to, p);
+  const int grid = (int)std::min<int64_t>(p.total_rows * CL, kNumSMs) / CL * CL;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(128 + EW * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  L2I_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tw, to, p));
   return check_launch("conv_tc_uprow");
 }
 
@@ -706,7 +733,10 @@ int launch_conv_tc_uprow(const void* in, const __nv_bfloat16* w, const ConvGeom&
   UprowParams p{};
   p.B = g.B; p.H = g.H; p.W = g.W; p.Cout = Cout; p.e = e;
   p.nch = Cout / CO; p.nseg = g.W / kSegW;
-  p.total_rows = (int64_t)g.B * p.nch * p.nseg * g.H;
+  // CTA pairs (streamed weights, even batch): the two CTAs of a cluster take samples b and b + B / 2 of the same row range
+  const bool pair = g_switches.cluster && CO == 64 && g.B % 2 == 0;
+  p.b_pair_off = pair ? g.B / 2 : 0;
+  p.total_rows = (int64_t)(pair ? g.B / 2 : g.B) * p.nch * p.nseg * g.H;
   CUtensorMap ta, tw, to;
   {
     const uint64_t dims[4] = {(uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
@@ -717,7 +747,7 @@ int launch_conv_tc_uprow(const void* in, const __nv_bfloat16* w, const ConvGeom&
   {
     const uint64_t dims[3] = {(uint64_t)g.Cin, (uint64_t)(2 * CO), (uint64_t)(9 * p.nch)};
     const uint64_t str[3] = {2, (uint64_t)g.Cin * 2, (uint64_t)2 * CO * g.Cin * 2};
-    const uint32_t box[3] = {64, (uint32_t)(2 * CO), 1};
+    const uint32_t box[3] = {64, (uint32_t)(pair ? CO : 2 * CO), 1};   // a CTA of a pair loads half of a tile's rows
     L2I_TRY(make_tmap(&tw, w, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
   }
   {
@@ -728,10 +758,12 @@ int launch_conv_tc_uprow(const void* in, const __nv_bfloat16* w, const ConvGeom&
     const uint32_t estr[4] = {1, 2, 1, 1};
     L2I_TRY(make_tmap_strided(&to, e.out, 4, dims, str, box, estr, CU_TENSOR_MAP_SWIZZLE_NONE));
   }
-  if (CO == 32) return launch_uprow_variant<32, 1, 4, true, 1, 1, 8>(ta, tw, to, p, st);
-  if (g.Cin == 128) return launch_uprow_variant<64, 2, 2, false, 2, 4, 8>(ta, tw, to, p, st);
+  if (CO == 32) return launch_uprow_variant<32, 1, 4, true, 1, 1, 8, 1>(ta, tw, to, p, st);
+  if (g.Cin == 128) return pair ? launch_uprow_variant<64, 2, 2, false, 2, 4, 8, 2>(ta, tw, to, p, st)
+                                : launch_uprow_variant<64, 2, 2, false, 2, 4, 8, 1>(ta, tw, to, p, st);
   // Cin = 256: two input rows are 136 KB, which leaves a 4 x 16 KB weight ring (one 64-channel plane per stage)
-  return launch_uprow_variant<64, 4, 2, false, 1, 4, 8>(ta, tw, to, p, st);
+  return pair ? launch_uprow_variant<64, 4, 2, false, 1, 4, 8, 2>(ta, tw, to, p, st)
+              : launch_uprow_variant<64, 4, 2, false, 1, 4, 8, 1>(ta, tw, to, p, st);
 }
 
 }  // namespace l2i
