@@ -295,15 +295,21 @@ def test_kernel_selection_sweep_bf16_vs_fp32(size, cm, batch):
 
 
 @pytest.mark.parametrize("env", [{"L2I_QUAD": "0"}, {"L2I_ARES": "0"}, {"L2I_FIR_SIMT": "1"}, {"L2I_HALO": "0", "L2I_QUAD": "0"},
-                                 {"L2I_COMPOSITE_RES": "4096"}])
+                                 {"L2I_COMPOSITE_RES": "4096"}, {"L2I_ARES_PAIR": "0"}, {"L2I_UPROW": "0"}, {"L2I_VPAIR": "0"},
+                                 {"L2I_CLUSTER": "1", "_batch": "2"}, {"_batch": "3"}])
 def test_fallback_kernel_paths_stay_correct(env, monkeypatch):
     """The kernel-selection switches (read at every generator create) route the same layers through the older kernels:
     pair-packed halo instead of the 2x2-block kernel, the general kernel instead of the A-resident / halo-resident ones,
-    the register-window FIR, and the two-kernel transposed conv + blur instead of the composite conv."""
+    the register-window FIR, the two-kernel transposed conv + blur instead of the composite conv, the one-tile A-resident
+    kernel instead of the tile-pair one, the composite instead of the row-marching up-conv; L2I_CLUSTER=1 takes the CTA-pair
+    (TMA-multicast weight ring) variant of the streamed-weight up-conv kernels, which needs an even batch; batch 3 crosses
+    sample boundaries inside the contiguous tile ranges of the tile-pair kernel."""
     from latent2im_b200.graphs.stylegan_v2_real.networks import Generator
+    env = dict(env)
+    batch = int(env.pop("_batch", "1"))
     for k, v in env.items():
         monkeypatch.setenv(k, v)
-    size, batch = 512, 1
+    size = 512
     gen = load_synthetic(Generator(size, 512, 2, channel_multiplier=1), seed=3, rgb_gain=0.25).cuda()
     z = torch.tensor(synthetic_z(batch, 1), dtype=torch.float32).cuda()
     lat = gen.style(z)[:, None, :].repeat(1, gen.n_latent, 1)
