@@ -10,7 +10,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def main(tag, n_forward_launches=22, batch=32):
+def main(tag, n_forward_launches=22, batch=32):  # 17 conv + 5 FIR launches of one forward (ncu -k regex:"conv_tc|fir_tma")
     go, pr = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
     rows = list(csv.reader(open(os.path.join(go, f"prof_{tag}_raw.csv"))))
     hdr, units, data = rows[0], rows[1], rows[2:]
@@ -29,8 +29,8 @@ def main(tag, n_forward_launches=22, batch=32):
         per.append({"id": int(d[ix["ID"]]), "kernel": name.replace("void l2i::<unnamed>::", "")[:60],
                     "ms": float(d[ix["gpu__time_duration.sum"]]) * tscale.get(units[ix["gpu__time_duration.sum"]], 1.0), "dram_bytes": b,
                     "tensor_pct": float(d[ix["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]])})
-    json.dump({"source": f"profiles/{tag}_ncu_full_summary.txt (ncu --set full --clock-control none, bench.py --steps 1 --warmup 1, "
-                         f"B={batch}, 1024px, first forward: launches 0-{n_forward_launches - 1})",
+    json.dump({"source": f"profiles/{tag}_ncu_full_summary.txt (ncu --set full --clock-control none -k regex:conv_tc|fir_tma, bench.py --steps 1 "
+                         f"--warmup 0, B={batch}, 1024px, first forward: the {n_forward_launches} conv / FIR launches)",
                "batch": batch, "conv_dram_bytes_per_image": conv / batch, "fir_dram_bytes_per_image": fir / batch, "launches": per},
               open(os.path.join(pr, "ncu_traffic.json"), "w"), indent=1)
     lines = [l for l in open(os.path.join(go, f"launches_{tag}.csv")) if not l.startswith("==")]

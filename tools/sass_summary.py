@@ -25,7 +25,7 @@ def main():
             continue
         if cur is None:
             continue
-        if re.match(r"\s+/\*[0-9a-f]{4}\*/", line):
+        if re.match(r"\s+/\*[0-9a-f]{4,}\*/", line):
             counts[cur]["instructions"] += 1
             for k, p in PAT.items():
                 if re.search(p, line):
