@@ -54,6 +54,10 @@ fir_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   __shared__ __align__(8) uint64_t bar;
   __shared__ float red[BWD ? CC : 1];
+  // forward: the tile's noise (16 rows x COLS columns, shared by all channel quads) is staged once while the TMA load is in flight;
+  // a global load per row in the marching loop was the kernel's top stall (ncu: long scoreboard 5.5 of 12.7 cycles per instruction -
+  // the loads cannot be hoisted over the previous row's stores)
+  __shared__ float noise_tile[BWD ? 1 : kFirRows * COLS];
 
   int r = blockIdx.x;
   const int tx = r % p.tiles_x; r /= p.tiles_x;
@@ -69,6 +73,13 @@ fir_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     tma_load_4d(smem, &tmap, &bar, c0, X0 + p.origin, Y0 + p.origin, b);
   }
   if (BWD && threadIdx.x < CC) red[threadIdx.x] = 0.f;
+  if (!BWD) {
+    for (int i = threadIdx.x; i < kFirRows * COLS; i += 256) {
+      const int ry = i / COLS, rx = i - ry * COLS;
+      const int Yn = Y0 + ry, Xn = X0 + rx;
+      noise_tile[i] = (p.noise != nullptr && Yn < p.OH && Xn < p.OW) ? __ldg(p.noise + (int64_t)b * p.noise_bs + (int64_t)Yn * p.OW + Xn) : 0.f;
+    }
+  }
   const int q = threadIdx.x % QUADS, x = threadIdx.x / QUADS;
   const int X = X0 + x, c = c0 + 4 * q;
   const bool col_ok = X < p.OW;
@@ -120,7 +131,7 @@ fir_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     }
     if (!col_ok) continue;
     if (!BWD) {
-      const float nz = p.noise != nullptr ? nw * __ldg(p.noise + (int64_t)b * p.noise_bs + (int64_t)Y * p.OW + X) : 0.f;
+      const float nz = nw * noise_tile[yy * COLS + x];
       B4 ov, yv;
       const uint64_t NZ = pk2(nz, nz);
 #pragma unroll
