@@ -13,6 +13,10 @@
 //                                           next-style scale/ToRGB/skip -> global stores
 // Pipelines: smem ring (full/empty mbarriers, TMA <-> MMA) and a 2-deep TMEM accumulator ring
 // (tmem_full/tmem_empty, MMA <-> epilogue) so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+
 #include "tc_epilogue.cuh"
 
 namespace l2i {
@@ -332,6 +336,27 @@ EncodeTiledFn get_encode_fn() {
 }  // namespace
 
 namespace tc {
+namespace {
+struct TmapKey {
+  const void* base;
+  int dt, rank, swz, pad;
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  bool operator==(const TmapKey& o) const { return std::memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) { h ^= w[i]; h *= 1099511628211ull; }
+    return (size_t)h;
+  }
+};
+static_assert(sizeof(TmapKey) % 8 == 0, "hashed as 64-bit words");
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+std::mutex g_tmap_mutex;
+}  // namespace
+
 static int make_tmap_typed(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
                            const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz,
                            const uint32_t* elem_strides = nullptr);
@@ -359,15 +384,27 @@ static int make_tmap_typed(CUtensorMap* map, CUtensorMapDataType dt, const void*
     set_error("conv_tc: cuTensorMapEncodeTiled entry point not available");
     return L2I_ERR_CUDA;
   }
-  cuuint64_t gdim[5], gstr[4];
-  cuuint32_t bx[5], es[5];
-  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = elem_strides ? elem_strides[i] : 1; }
-  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i + 1];
-  CUresult r = fn(map, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+  // Descriptors are cached by value of everything that goes into them: a forward encodes 2-5 maps per conv launch over the same few
+  // buffers, which is host time that matters for small batches (256 px, batch 4 is host-bound).
+  TmapKey key{};
+  key.base = base; key.dt = (int)dt; key.rank = rank; key.swz = (int)swz;
+  for (int i = 0; i < rank; ++i) { key.gdim[i] = dims[i]; key.bx[i] = box[i]; key.es[i] = elem_strides ? elem_strides[i] : 1; }
+  for (int i = 0; i + 1 < rank; ++i) key.gstr[i] = strides_bytes[i + 1];
+  {
+    std::lock_guard<std::mutex> lock(g_tmap_mutex);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) { *map = it->second; return L2I_OK; }
+  }
+  CUresult r = fn(map, dt, (cuuint32_t)rank, const_cast<void*>(base), key.gdim, key.gstr, key.bx, key.es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("conv_tc: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
     return L2I_ERR_CUDA;
+  }
+  {
+    std::lock_guard<std::mutex> lock(g_tmap_mutex);
+    if (g_tmap_cache.size() >= 8192) g_tmap_cache.clear();   // bounded: callers that stream through fresh buffers just re-encode
+    g_tmap_cache.emplace(key, *map);
   }
   return L2I_OK;
 }

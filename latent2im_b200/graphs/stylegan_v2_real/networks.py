@@ -156,7 +156,11 @@ class _NativeHandle:
         self.training = False
 
     def upload(self, gen):
-        version = tuple((p.data_ptr(), p._version) for p in gen.parameters())
+        # (data_ptr, version counter) of every parameter, read through a cached list of (module, name) slots: nn.Module.parameters()
+        # walks the module tree with de-duplication sets and cost 0.3 ms per call - a third of the host time of a 256-px batch-4
+        # forward (tools/probes/host_overhead.py).  In-place updates, load_state_dict, .to() and assigning a new Parameter to an
+        # existing module are all seen; replacing a whole sub-module is not (call gen.invalidate_native() after such surgery).
+        version = tuple((p.data_ptr(), p._version) for p in gen._param_list())
         if version == self.version:
             return
         with torch.cuda.device(self.device):
@@ -252,6 +256,19 @@ class Generator(nn.Module):
             self.max_batch = max(self.max_batch, int(max_batch))
         return self
 
+    def _param_list(self):
+        slots = self.__dict__.get("_param_slots")
+        if slots is None:
+            slots = [(m, n) for m in self.modules() for n in m._parameters]
+            object.__setattr__(self, "_param_slots", slots)
+        return [m._parameters[n] for m, n in slots if m._parameters.get(n) is not None]
+
+    def invalidate_native(self):
+        """Forget the cached parameter slots (after replacing sub-modules); the next forward re-checks every weight."""
+        self.__dict__.pop("_param_slots", None)
+        for h in self._native.values():
+            h.version = None
+
     def _handle(self, device, batch):
         if device.type != "cuda":
             raise RuntimeError("input must be a CUDA tensor")  # reference ops: TORCH_CHECK(is_cuda)
@@ -296,6 +313,7 @@ class Generator(nn.Module):
     def __getstate__(self):
         state = self.__dict__.copy()
         state["_native"] = {}
+        state.pop("_param_slots", None)
         state.pop("_last", None)
         state.pop("_last_train", None)
         return state
