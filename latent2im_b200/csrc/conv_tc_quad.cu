@@ -35,11 +35,19 @@ constexpr int kQRowPitch = kQHaloPairs * 128;             // 1280 bytes per halo
 constexpr int kQHaloBytes = kQHaloH * kQRowPitch;         // 43520
 constexpr int kQStageBytes = (kQHaloBytes + 1023) & ~1023;
 constexpr int kQStages = 2;
-constexpr int kQGroups = 2;                               // 384 threads; two tile epilogues in flight keep up with the MMAs
-constexpr int kQTmemCols = 256;                           // 2 accumulators x 128 columns
+// Three epilogue warpgroups (round 2): the layer is bound by its epilogue's instruction stream (trimming the MMAs by 12 % changed
+// nothing), two groups at 166 registers could not keep up with the MMAs.  512 threads launch with 128 registers each; the
+// producer / MMA warpgroup gives its surplus to the epilogue warps (setmaxnreg 40 / 152).
+constexpr int kQGroups = 3;
+constexpr int kQTmemCols = 512;                           // 3 accumulators x 128 columns (power-of-two allocation)
 constexpr int kQThreads = 128 + kQGroups * 128;
+constexpr int kQRegLow = 40, kQRegHigh = 152;
+static_assert(128 * kQRegLow + kQGroups * 128 * kQRegHigh <= kQThreads * 128, "setmaxnreg budget");
 constexpr int kQN = 128, kQK = 512;
-constexpr int kQWBytes = kQN * kQK * 2;                   // 131072
+// resident weights: patch rows 1, 2 as four [128 n][64 k] atoms, rows 0 / 3 (which reach only the upper / lower pixel row of a
+// block) as four [64 n][64 k] half atoms: 4 x 16 KB + 4 x 8 KB
+constexpr int kQWideAtom = kQN * 128, kQHalfAtom = (kQN / 2) * 128;
+constexpr int kQWBytes = 4 * kQWideAtom + 4 * kQHalfAtom;   // 98304
 constexpr int kQSkipW = 16, kQSkipH = kQTileH / 2 + 2;     // low-res skip patch: columns n0-4 .. n0+11 (TMA needs a 16-byte aligned start), rows m0-1 .. m0+16
 constexpr int kQSkipFloats = 3 * kQSkipH * kQSkipW;        // 864 floats = 3456 bytes per accumulator stage
 constexpr int kQSkipStride = (kQSkipFloats + 31) & ~31;    // buffers 128-byte aligned (TMA destination)
@@ -48,7 +56,7 @@ constexpr int kQSmem = kQStages * kQStageBytes + kQWBytes + 1024;
 struct QuadParams {
   int B, H, W;
   int tiles_x, tiles_y, total_tiles;
-  uint32_t idesc;
+  uint32_t idesc, idesc64;
   int has_skip;            // tmap_s is valid: the producer loads the low-res skip patch of every tile
   EpiParams e;
 };
@@ -68,6 +76,7 @@ __device__ __forceinline__ void quad_group_sync(int group) {
 
 __global__ void __launch_bounds__(kQThreads, 1)
 conv_tc_quad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                    const __grid_constant__ CUtensorMap tmap_wh,
                     const __grid_constant__ CUtensorMap tmap_s, const __grid_constant__ QuadParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -108,11 +117,17 @@ conv_tc_quad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     x0 = tx * kQTileW; y0 = ty * kQTileH;
   };
 
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kQRegLow));
   if (warp == 0) {
     // ===================== TMA producer: the weight matrix once, then one halo tile per output tile =====
     if (lane == 0) {
       mbar_expect_tx(&w_bar, (uint32_t)kQWBytes);
-      for (int t = 0; t < kQK / 64; ++t) tma_load_3d(smem_w + t * (kQN * 128), &tmap_w, &w_bar, 0, 0, t);
+      for (int t = 0; t < 4; ++t) tma_load_3d(smem_w + t * kQWideAtom, &tmap_w, &w_bar, 0, 0, 2 + t);        // patch rows 1, 2
+      for (int t = 0; t < 2; ++t) {
+        tma_load_3d(smem_w + 4 * kQWideAtom + t * kQHalfAtom, &tmap_wh, &w_bar, 0, 0, t);                     // row 0: weight rows 0..63
+        tma_load_3d(smem_w + 4 * kQWideAtom + (2 + t) * kQHalfAtom, &tmap_wh, &w_bar, 0, kQN / 2, 6 + t);      // row 3: rows 64..127
+      }
       int stage = 0;
       uint32_t phase_bit = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -159,14 +174,24 @@ conv_tc_quad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const uint64_t a_desc0 = kmajor_desc_at(kHiA, smem_a0 + (uint32_t)(stage * kQStageBytes));
         const uint32_t tmem_d = tmem_u + (uint32_t)(grp * kQN);
         if (elect_one()) {
+          // Patch rows 1 and 2 feed both pixel rows of the block (N = 128); row 0 only reaches the upper pixels (a = 0: accumulator
+          // columns 0..63, weight rows 0..63) and row 3 only the lower ones (a = 1: columns / rows 64..127) - their other halves are
+          // structural zeros, so they are N = 64 MMAs: 48 instead of 64 clocks and 6 instead of 8 KB of operands each.  Rows 1, 2 go
+          // first: the first MMA initialises all 128 columns.
 #pragma unroll
-          for (int r = 0; r < 4; ++r) {
+          for (int ri = 0; ri < 4; ++ri) {
+            const int r = ri == 0 ? 1 : (ri == 1 ? 2 : (ri == 2 ? 0 : 3));
+            const bool wide = r == 1 || r == 2;
+            const uint32_t half = r == 3 ? 64u : 0u;              // accumulator column offset of the N = 64 MMAs
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
               // A: rows = blocks along x (128 B apart), 8-row groups = block rows (two image rows apart)
               // B: K-major [128 x 64] atoms, atom = (r*128 + kk*16) / 64
-              umma_bf16(tmem_d, a_desc0 + (uint64_t)((r * kQRowPitch + 64 + kk * 32) >> 4),
-                        b_desc0 + (uint64_t)(((r * 2 + (kk >> 2)) * (kQN * 128) + (kk & 3) * 32) >> 4), p.idesc, (r | kk) != 0 ? 1u : 0u);
+              const int j = kk >> 2;                              // 64-channel atom of the patch row
+              const int woff = r == 1 ? j * kQWideAtom : (r == 2 ? (2 + j) * kQWideAtom
+                                                                 : 4 * kQWideAtom + ((r == 0 ? 0 : 2) + j) * kQHalfAtom);
+              umma_bf16(tmem_d + half, a_desc0 + (uint64_t)((r * kQRowPitch + 64 + kk * 32) >> 4),
+                        b_desc0 + (uint64_t)((woff + (kk & 3) * 32) >> 4), wide ? p.idesc : p.idesc64, (ri | kk) != 0 ? 1u : 0u);
             }
           }
           umma_commit(&empty_bar[stage]);
@@ -176,7 +201,9 @@ conv_tc_quad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (++grp == kQGroups) { grp = 0; grp_phase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kQRegHigh));
     // ===================== epilogue =====================
     const EpiParams& e = p.e;
     const int group = (warp - 4) >> 2;
@@ -388,6 +415,7 @@ int launch_conv_tc_quad(const void* in, const __nv_bfloat16* w, const ConvGeom& 
   QuadParams p{};
   p.B = g.B; p.H = g.H; p.W = g.W; p.e = e;
   p.idesc = make_idesc_bf16(128, kQN, 0);
+  p.idesc64 = make_idesc_bf16(128, kQN / 2, 0);
   CUtensorMap ta, tw;
   {
     const uint64_t dims[4] = {64, (uint64_t)g.W / 2, (uint64_t)g.H, (uint64_t)g.B};   // horizontal pixel pairs
@@ -400,6 +428,13 @@ int launch_conv_tc_quad(const void* in, const __nv_bfloat16* w, const ConvGeom& 
     const uint64_t str[3] = {2, 128, (uint64_t)kQN * 128};
     const uint32_t box[3] = {64, kQN, 1};
     L2I_TRY(make_tmap(&tw, w, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  CUtensorMap twh;
+  {
+    const uint64_t dims[3] = {64, kQN, kQK / 64};
+    const uint64_t str[3] = {2, 128, (uint64_t)kQN * 128};
+    const uint32_t box[3] = {64, kQN / 2, 1};
+    L2I_TRY(make_tmap(&twh, w, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
   }
   CUtensorMap ts = ta;   // placeholder when there is no skip image (first ToRGB of a network never reaches this kernel)
   p.has_skip = (e.fused_skip && e.skip_in != nullptr) ? 1 : 0;
@@ -421,7 +456,7 @@ int launch_conv_tc_quad(const void* in, const __nv_bfloat16* w, const ConvGeom& 
     attr_set = true;
   }
   const int grid = std::min(p.total_tiles, kNumSMs);
-  conv_tc_quad_kernel<<<grid, kQThreads, kQSmem, st>>>(ta, tw, ts, p);
+  conv_tc_quad_kernel<<<grid, kQThreads, kQSmem, st>>>(ta, tw, twh, ts, p);
   return check_launch("conv_tc_quad");
 }
 
