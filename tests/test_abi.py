@@ -47,3 +47,32 @@ def test_state_dict_layout_matches_reference():
         g = Generator(int(size), 512, 8)
         mine = [[k, list(v.shape)] for k, v in g.state_dict().items()]
         assert mine == keys
+
+
+def test_weight_version_check_sees_every_kind_of_update():
+    """The per-call weight-version check reads (data_ptr, version) through cached (module, name) slots instead of walking
+    nn.Module.parameters(): in-place updates, load_state_dict and a Parameter assigned to an existing module must all change
+    the fingerprint; invalidate_native() forgets the cache (sub-module surgery)."""
+    import torch
+    from latent2im_b200.graphs.stylegan_v2_real.networks import Generator
+    gen = Generator(16, 32, 2)
+
+    def fingerprint():
+        return tuple((p.data_ptr(), p._version) for p in gen._param_list())
+
+    assert len(gen._param_list()) == len(list(gen.parameters()))
+    assert {id(p) for p in gen._param_list()} == {id(p) for p in gen.parameters()}
+    f0 = fingerprint()
+    assert fingerprint() == f0
+    with torch.no_grad():
+        gen.conv1.conv.weight.mul_(1.5)                       # in-place update: version counter
+    f1 = fingerprint()
+    assert f1 != f0
+    gen.load_state_dict({k: v.clone() for k, v in gen.state_dict().items()})   # copy_ into the same storage: version counter
+    f2 = fingerprint()
+    assert f2 != f1
+    gen.conv1.conv.weight = torch.nn.Parameter(gen.conv1.conv.weight.detach().clone())   # new Parameter on an existing module
+    f3 = fingerprint()
+    assert f3 != f2 and {id(p) for p in gen._param_list()} == {id(p) for p in gen.parameters()}
+    gen.invalidate_native()
+    assert "_param_slots" not in gen.__dict__ and fingerprint() == f3
