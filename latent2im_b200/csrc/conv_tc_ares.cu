@@ -605,6 +605,225 @@ int launch_ares_variant(const CUtensorMap& ta, const CUtensorMap& tw, const Ares
   return check_launch("conv_tc_ares");
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Halo RING for the wide plain layers (Cin = 256 / 512, N = 256 output channels per tile; 512 -> 512 @ 64^2, 256 -> 256 @ 128^2 ...).
+// The general kernel (conv_tc.cu) reloads the 16 KB activation tile for every (tap, 64-channel chunk): its TMA fills (A + B, each
+// byte written once and read once) cost as many shared-memory wavefronts as the MMA operand reads, and the layer's time equals
+// the wavefront count of that pipe (65 k per tile at 512 -> 512, measured = computed).  Here the loop order is chunk-outer /
+// tap-inner: ONE (8+2) x (16+2) halo plane per 64-channel chunk serves all nine taps (UMMA descriptors at tap-shifted start
+// addresses, as above), planes cycle through a three-slot ring with their own full / empty barriers so the next tile's planes
+// arrive while this tile's last chunks are multiplied; only the [256][64] weight tiles stream per (chunk, tap).
+// A fills per tile: 9 x 16 KB per chunk -> 23 KB per chunk.
+constexpr int kHASlots = 3;
+constexpr int kHN = 256;
+
+template <int WST>
+__global__ void __launch_bounds__(128 + 2 * 128, 1)
+conv_tc_hring_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                     const __grid_constant__ AresParams p, const int KC, const int tiles_n) {
+  constexpr int N = kHN, GROUPS = 2, CO = kHN;
+  constexpr int kBStageBytes = N * 128;                 // one (chunk, tap) weight tile
+  constexpr int kEpiFloats = 6 * CO;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem_b = smem + kHASlots * kRPlaneStride;
+  __shared__ __align__(16) float epi_smem[GROUPS * kEpiFloats];
+  __shared__ __align__(8) uint64_t a_full[kHASlots];
+  __shared__ __align__(8) uint64_t a_empty[kHASlots];
+  __shared__ __align__(8) uint64_t w_full[WST];
+  __shared__ __align__(8) uint64_t w_empty[WST];
+  __shared__ __align__(8) uint64_t tmem_full[GROUPS];
+  __shared__ __align__(8) uint64_t tmem_empty[GROUPS];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kHASlots; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < WST; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int a = 0; a < GROUPS; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  // contiguous tile range per CTA, channel tile fastest: the N tiles of one pixel tile follow each other (halo planes hot in L2)
+  const int t_begin = (int)((int64_t)p.total_tiles * blockIdx.x / gridDim.x);
+  const int t_end = (int)((int64_t)p.total_tiles * (blockIdx.x + 1) / gridDim.x);
+  auto decode = [&](int tile, int& nt, int& x0, int& y0, int& b) {
+    nt = tile % tiles_n;
+    int r = tile / tiles_n;
+    const int tx = r % p.tiles_x;
+    r /= p.tiles_x;
+    const int ty = r % p.tiles_y;
+    b = r / p.tiles_y;
+    x0 = tx * kRTileW; y0 = ty * kRTileH;
+  };
+
+  if (warp == 0) {
+    // ===================== A producer: one halo plane per (tile, 64-channel chunk) =====================
+    if (lane == 0) {
+      uint32_t acnt = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        int nt, x0, y0, b;
+        decode(tile, nt, x0, y0, b);
+        for (int kc = 0; kc < KC; ++kc, ++acnt) {
+          const int slot = acnt % kHASlots;
+          mbar_wait(&a_empty[slot], ((acnt / kHASlots) & 1) ^ 1);
+          mbar_expect_tx(&a_full[slot], kRPlaneBytes);
+          tma_load_4d(smem + slot * kRPlaneStride, &tmap_a, &a_full[slot], kc * 64, x0 - 1, y0 - 1, b);
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== B producer: the [256][64] weight tile of every (chunk, tap), same order as the MMA issuer ==========
+    if (lane == 0) {
+      uint32_t wcnt = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        int nt, x0, y0, b;
+        decode(tile, nt, x0, y0, b);
+        for (int kc = 0; kc < KC; ++kc)
+          for (int t = 0; t < 9; ++t, ++wcnt) {
+            const int ws = wcnt % WST;
+            mbar_wait(&w_empty[ws], ((wcnt / WST) & 1) ^ 1);
+            mbar_expect_tx(&w_full[ws], kBStageBytes);
+            tma_load_3d(smem_b + ws * kBStageBytes, &tmap_w, &w_full[ws], kc * 64, nt * N, t);
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: warp-uniform control flow, one elected lane issues (tc_ptx.cuh: elect_one) =============
+    uint32_t acnt = 0, wcnt = 0;
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t smem_a0 = smem_u32(smem), smem_b0 = smem_u32(smem_b);
+    constexpr uint64_t kHiA = kmajor_desc_hi(kRW * 128, 2), kHiB = kmajor_desc_hi(1024, 2);
+    int it = 0;
+    for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+      const int acc = it & 1;
+      mbar_wait(&tmem_empty[acc], (((uint32_t)it >> 1) & 1u) ^ 1u);
+      const uint32_t tmem_d = tmem_u + (uint32_t)(acc * N);
+      for (int kc = 0; kc < KC; ++kc, ++acnt) {
+        const int slot = acnt % kHASlots;
+        mbar_wait(&a_full[slot], (acnt / kHASlots) & 1);
+        const uint32_t a_base = smem_a0 + (uint32_t)(slot * kRPlaneStride);
+#pragma unroll 1
+        for (int t = 0; t < 9; ++t, ++wcnt) {
+          const int ws = wcnt % WST;
+          const uint32_t shift = (uint32_t)(((t / 3) * kRW + (t % 3)) * 128);   // tap (dy, dx) = (t/3 - 1, t%3 - 1)
+          mbar_wait(&w_full[ws], (wcnt / WST) & 1);
+          tc_fence_after();
+          const uint64_t a_desc = kmajor_desc_at(kHiA, a_base + shift);
+          const uint64_t b_desc = kmajor_desc_at(kHiB, smem_b0 + (uint32_t)(ws * kBStageBytes));
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_d, a_desc + (uint64_t)((k * 32) >> 4), b_desc + (uint64_t)((k * 32) >> 4), p.idesc, (kc | t | k) != 0 ? 1u : 0u);
+            umma_commit(&w_empty[ws]);
+          }
+        }
+        if (elect_one()) umma_commit(&a_empty[slot]);
+      }
+      if (elect_one()) umma_commit(&tmem_full[acc]);
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (one pixel x 256 channels per lane, as conv_tc_ares_kernel) =====================
+    const EpiParams& e = p.e;
+    const int group = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int gtid = threadIdx.x - (128 + group * 128);
+    float* sp = epi_smem + group * kEpiFloats;
+    float* s_d = sp;
+    float* s_b = sp + CO;
+    float* s_n = sp + 2 * CO;
+    float* s_w = sp + 3 * CO;
+    constexpr float kSqrt2 = 1.4142135623730951f;
+    const float nw = (e.noise != nullptr && e.noise_w != nullptr) ? __ldg(e.noise_w) * kSqrt2 : 0.f;
+    const int64_t plane = (int64_t)p.out_H * p.out_W;
+    const int lx = row & 7, ly = row >> 3;
+    uint32_t grp_phase = 0;
+    int staged_key = -1;
+    for (int it = group; t_begin + it < t_end; it += GROUPS) {
+      int nt, x0, y0, b;
+      decode(t_begin + it, nt, x0, y0, b);
+      const int ox = x0 + lx, oy = y0 + ly;
+      const bool ok = ox < p.W && oy < p.H;
+      const int co0 = nt * N;
+
+      if (b * tiles_n + nt != staged_key) {
+        ares_group_sync(group);
+        for (int j = gtid; j < CO; j += 128) {
+          s_d[j] = (e.demod != nullptr ? __ldg(e.demod + (int64_t)b * e.demod_bs + co0 + j) : 1.f) * kSqrt2;
+          s_b[j] = __ldg(e.bias + co0 + j) * kSqrt2;
+          s_n[j] = e.s_next ? __ldg(e.s_next + (int64_t)b * e.s_next_bs + co0 + j) : 1.f;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) s_w[c * CO + j] = e.wr ? __ldg(e.wr + (int64_t)b * e.wr_bs + c * p.Cout + co0 + j) : 0.f;
+        }
+        ares_group_sync(group);
+        staged_key = b * tiles_n + nt;
+      }
+
+      float nz = 0.f;
+      float up[3] = {0.f, 0.f, 0.f};
+      if (ok && e.noise != nullptr) nz = nw * __ldg(e.noise + (int64_t)b * e.noise_bs + (int64_t)oy * p.out_W + ox);
+      if (ok && e.fused_skip) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          up[c] = __ldg(e.rgb_bias + c);
+          if (e.skip_in != nullptr)
+            up[c] += upsample2x_at(e.skip_in + ((int64_t)b * 3 + c) * (plane / 4), p.out_H / 2, p.out_W / 2, oy, ox, e.fir);
+        }
+      }
+
+      mbar_wait(&tmem_full[it & 1], grp_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((it & 1) * N);
+      float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
+      const int64_t pix = ((int64_t)b * p.out_H + oy) * p.out_W + ox;
+#pragma unroll 1
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        __nv_bfloat16* outc = nullptr;
+        __nv_bfloat16* yc = nullptr;
+        if (ok) {
+          if (e.out != nullptr && e.s_next != nullptr) outc = (__nv_bfloat16*)e.out + pix * p.Cout + co0 + c0;
+          if (e.y_out != nullptr) yc = (__nv_bfloat16*)e.y_out + pix * p.Cout + co0 + c0;
+        }
+        tmem_ld_wait();
+        epilogue_chunk32<EPI_ACT_RGB>(v, s_d + c0, s_b + c0, s_n + c0, s_w + c0, s_w + CO + c0, s_w + 2 * CO + c0, nz, false, rgb0, rgb1,
+                                      rgb2, outc, yc);
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[it & 1]);
+      grp_phase ^= 1;
+
+      if (e.wr != nullptr && ok) {
+        const float r3[3] = {rgb0, rgb1, rgb2};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          if (e.fused_skip) e.skip_out[((int64_t)b * 3 + c) * plane + (int64_t)oy * p.out_W + ox] = r3[c] + up[c];
+          else e.rgb_part[(((int64_t)nt * p.B + b) * 3 + c) * plane + (int64_t)oy * p.out_W + ox] = r3[c];
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace
 
 bool conv_tc_ares_supported(const ConvGeom& g, const EpiParams& e) {
@@ -653,6 +872,53 @@ int launch_conv_tc_ares(const void* in, const __nv_bfloat16* w, const ConvGeom& 
     return launch_ares_pair<3>(ta, tw, to, p, st);
   }
   return launch_ares_variant<128, 2, 2, 3, 2, EPI_ACT_RGB, false>(ta, tw, p, st);
+}
+
+// Wide plain layers (act + ToRGB epilogue): Cin a multiple of 64 from 256 up, Cout a multiple of 256, unsplit weights.
+bool conv_tc_hring_supported(const ConvGeom& g, const EpiParams& e) {
+  if (!g_switches.hring || !tmap_available()) return false;
+  if (g.nphase != 1 || g.in_scale != 1 || g.weight_taps != 9 || g.in_pair_packed || g.out_pair_packed || g.up_cout != 0) return false;
+  if (g.Cin < 256 || g.Cin % 64 != 0 || g.Cout % kHN != 0 || g.H < 16 || g.W < 8 || e.mode != 0 || e.wr == nullptr) return false;
+  return g.OH == g.H && g.OW == g.W;
+}
+
+// w: [9][Cout][Cin] bf16 (the general kernel's packing)
+int launch_conv_tc_hring(const void* in, const __nv_bfloat16* w, const ConvGeom& g, const EpiParams& e, cudaStream_t st) {
+  AresParams p{};
+  p.B = g.B; p.H = g.H; p.W = g.W; p.out_H = g.out_H; p.out_W = g.out_W; p.e = e;
+  p.Cout = g.Cout;
+  p.idesc = make_idesc_bf16(128, kHN, 0);
+  const int tiles_n = g.Cout / kHN;
+  if (e.fused_skip && tiles_n != 1) { set_error("conv_tc_hring: fused skip needs a single N tile"); return L2I_ERR_INVALID_ARG; }
+  CUtensorMap ta, tw;
+  {
+    const uint64_t dims[4] = {(uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
+    const uint64_t str[4] = {2, (uint64_t)g.Cin * 2, (uint64_t)g.W * g.Cin * 2, (uint64_t)g.H * g.W * g.Cin * 2};
+    const uint32_t box[4] = {64, kRW, kRH, 1};
+    L2I_TRY(make_tmap(&ta, in, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)g.Cin, (uint64_t)g.Cout, 9};
+    const uint64_t str[3] = {2, (uint64_t)g.Cin * 2, (uint64_t)g.Cout * g.Cin * 2};
+    const uint32_t box[3] = {64, kHN, 1};
+    L2I_TRY(make_tmap(&tw, w, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  p.tiles_x = ceil_div(g.W, kRTileW); p.tiles_y = ceil_div(g.H, kRTileH);
+  const int64_t total = (int64_t)p.tiles_x * p.tiles_y * g.B * tiles_n;
+  if (total <= 0 || total > 0x7fffffff) { set_error("conv_tc_hring: bad tile count"); return L2I_ERR_INVALID_ARG; }
+  p.total_tiles = (int)total;
+  constexpr int WST = 4;   // 4 x 512 MMA clocks in flight cover the L2 latency of a weight tile; three halo planes = 3 x 4608 clocks
+  constexpr int smem = kHASlots * kRPlaneStride + WST * kHN * 128 + 1024;
+  static_assert(smem + 2 * 6 * kHN * 4 + 512 <= 227 * 1024, "shared memory budget (dynamic + static epilogue vectors)");
+  auto kern = conv_tc_hring_kernel<WST>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    L2I_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int grid = std::min(p.total_tiles, kNumSMs);
+  kern<<<grid, 128 + 2 * 128, smem, st>>>(ta, tw, p, g.Cin / 64, tiles_n);
+  return check_launch("conv_tc_hring");
 }
 
 }  // namespace l2i

@@ -98,6 +98,7 @@ int run_conv(l2i_generator* g, const StyledConvLayer& L, const void* in, const C
   if (want_tc && !L.split && L.w_vpair != nullptr && conv_tc_vpair_supported(geom, e)) return launch_conv_tc_vpair(in, L.w_vpair, geom, e, st);
   if (want_tc && !L.split && conv_tc_halo_supported(geom, e) && (geom.Cin != 32 || (L.w_pair != nullptr && geom.in_pair_packed)))
     return launch_conv_tc_halo(in, geom.Cin == 32 ? L.w_pair : L.w_bf16, geom, e, st);
+  if (want_tc && !L.split && conv_tc_hring_supported(geom, e)) return launch_conv_tc_hring(in, L.w_bf16, geom, e, st);
   if (want_tc && conv_tc_supported(geom, e)) {
     if (!L.split) return launch_conv_tc(in, L.w_bf16, geom, e, st);
     // split-bf16 weights: every tap is issued twice, against the hi and the lo half of the weight tensor

@@ -18,6 +18,8 @@ int launch_conv_tc_halo(const void* in, const __nv_bfloat16* w, const ConvGeom& 
 int launch_pack_pair_weight(__nv_bfloat16* dst, const float* src, int Cout, float scale, cudaStream_t st);
 bool conv_tc_ares_supported(const ConvGeom& g, const EpiParams& e);
 int launch_conv_tc_ares(const void* in, const __nv_bfloat16* w, const ConvGeom& g, const EpiParams& e, cudaStream_t st);
+bool conv_tc_hring_supported(const ConvGeom& g, const EpiParams& e);
+int launch_conv_tc_hring(const void* in, const __nv_bfloat16* w, const ConvGeom& g, const EpiParams& e, cudaStream_t st);
 bool conv_tc_vpair_supported(const ConvGeom& g, const EpiParams& e);
 int launch_conv_tc_vpair(const void* in, const __nv_bfloat16* w, const ConvGeom& g, const EpiParams& e, cudaStream_t st);
 int launch_pack_vpair_weight(__nv_bfloat16* dst, const float* src, float scale, cudaStream_t st);

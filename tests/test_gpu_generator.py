@@ -295,13 +295,13 @@ def test_kernel_selection_sweep_bf16_vs_fp32(size, cm, batch):
 
 
 @pytest.mark.parametrize("env", [{"L2I_QUAD": "0"}, {"L2I_ARES": "0"}, {"L2I_FIR_SIMT": "1"}, {"L2I_HALO": "0", "L2I_QUAD": "0"},
-                                 {"L2I_COMPOSITE_RES": "4096"}, {"L2I_ARES_PAIR": "0"}, {"L2I_UPROW": "0"}, {"L2I_VPAIR": "0"},
+                                 {"L2I_COMPOSITE_RES": "4096"}, {"L2I_ARES_PAIR": "0"}, {"L2I_HRING": "0"}, {"L2I_UPROW": "0"}, {"L2I_VPAIR": "0"},
                                  {"L2I_CLUSTER": "1", "_batch": "2"}, {"_batch": "3"}])
 def test_fallback_kernel_paths_stay_correct(env, monkeypatch):
     """The kernel-selection switches (read at every generator create) route the same layers through the older kernels:
     pair-packed halo instead of the 2x2-block kernel, the general kernel instead of the A-resident / halo-resident ones,
     the register-window FIR, the two-kernel transposed conv + blur instead of the composite conv, the one-tile A-resident
-    kernel instead of the tile-pair one, the composite instead of the row-marching up-conv; L2I_CLUSTER=1 takes the CTA-pair
+    kernel instead of the tile-pair one, the general kernel instead of the halo-ring kernel of the wide plain layers, the composite instead of the row-marching up-conv; L2I_CLUSTER=1 takes the CTA-pair
     (TMA-multicast weight ring) variant of the streamed-weight up-conv kernels, which needs an even batch; batch 3 crosses
     sample boundaries inside the contiguous tile ranges of the tile-pair kernel."""
     from latent2im_b200.graphs.stylegan_v2_real.networks import Generator
