@@ -35,6 +35,7 @@ void refresh_kernel_switches() {
   s.cluster = flag("L2I_CLUSTER", 0);
   s.ares_pair = flag("L2I_ARES_PAIR", 1) != 0;
   s.hring = flag("L2I_HRING", 1) != 0;
+  s.hring_store = flag("L2I_HRING_STORE", 1) != 0;
   g_switches = s;
 }
 

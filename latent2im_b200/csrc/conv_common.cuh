@@ -21,11 +21,12 @@ namespace l2i {
 //   L2I_HALO=0, L2I_HALO_MASK=<bits: 1 plain Cin=64, 2 up-conv, 4 pair-packed Cin=32, 8 composite>, L2I_QUAD=0, L2I_ARES=0, L2I_VPAIR=0,
 //   L2I_UPROW=0 (composite 6x6 up-conv kernels instead of the row-marching fused up-conv), L2I_UPROW_MASK=<bits: 1 64->32, 2 128->64, 4 256->128>,
 //   L2I_CLUSTER=1 (experiment: CTA pairs with TMA-multicast weight rings in the weight-streaming kernels; measured no gain),
+//   L2I_HRING_STORE=0 (direct 16-byte stores instead of staging + TMA tensor stores in the halo-ring kernel),
 //   L2I_HRING=0 (general kernel instead of the halo-ring kernel for the plain layers with Cin >= 256),
 //   L2I_ARES_PAIR=0 (one-tile-per-epilogue A-resident kernel for the plain 128 -> 128 layer),
 //   L2I_FIR_SIMT=1 (register-window FIR kernels instead of the TMA-fed ones), L2I_HALO_BASE_OFFSET=1 (descriptor experiment)
 struct KernelSwitches {
-  int halo = 1, halo_mask = 15, halo_base_offset = 0, quad = 1, ares = 1, vpair = 1, fir_simt = 0, uprow = 1, uprow_mask = 7, cluster = 0, ares_pair = 1, hring = 1;
+  int halo = 1, halo_mask = 15, halo_base_offset = 0, quad = 1, ares = 1, vpair = 1, fir_simt = 0, uprow = 1, uprow_mask = 7, cluster = 0, ares_pair = 1, hring = 1, hring_store = 1;
 };
 extern KernelSwitches g_switches;
 void refresh_kernel_switches();

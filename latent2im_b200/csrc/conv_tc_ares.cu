@@ -620,7 +620,8 @@ constexpr int kHN = 256;
 template <int WST>
 __global__ void __launch_bounds__(128 + 2 * 128, 1)
 conv_tc_hring_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                     const __grid_constant__ AresParams p, const int KC, const int tiles_n) {
+                     const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ AresParams p, const int KC, const int tiles_n,
+                     const int tma_store) {
   constexpr int N = kHN, GROUPS = 2, CO = kHN;
   constexpr int kBStageBytes = N * 128;                 // one (chunk, tap) weight tile
   constexpr int kEpiFloats = 6 * CO;
@@ -628,6 +629,7 @@ conv_tc_hring_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_b = smem + kHASlots * kRPlaneStride;
+  uint8_t* smem_out = smem_b + WST * kBStageBytes;     // per epilogue warp: 32 pixels x 32 channels, SWIZZLE_64B rows (TMA store source)
   __shared__ __align__(16) float epi_smem[GROUPS * kEpiFloats];
   __shared__ __align__(8) uint64_t a_full[kHASlots];
   __shared__ __align__(8) uint64_t a_empty[kHASlots];
@@ -750,6 +752,12 @@ conv_tc_hring_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     const int lx = row & 7, ly = row >> 3;
     uint32_t grp_phase = 0;
     int staged_key = -1;
+    // 16-byte stores at pixel pitch (512 B) are one L1 wavefront per lane: 4096 per tile next to the MMA operand traffic.  The
+    // activation leaves through a per-warp staging tile and one TMA tensor store per 32-channel chunk instead (2 x 512 wavefronts).
+    uint8_t* stage_tile = smem_out + (warp - 4) * 2048;
+    __nv_bfloat16* stage_row = (__nv_bfloat16*)stage_tile + lane * 32;     // this lane's 64-byte row
+    const int stage_swz = (lane >> 1) & 3;                                 // SWIZZLE_64B: 16-byte piece ^= address bits [7:8]
+    const bool staged_out = tma_store != 0 && e.out != nullptr && e.s_next != nullptr;
     for (int it = group; t_begin + it < t_end; it += GROUPS) {
       int nt, x0, y0, b;
       decode(t_begin + it, nt, x0, y0, b);
@@ -794,12 +802,22 @@ conv_tc_hring_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         __nv_bfloat16* outc = nullptr;
         __nv_bfloat16* yc = nullptr;
         if (ok) {
-          if (e.out != nullptr && e.s_next != nullptr) outc = (__nv_bfloat16*)e.out + pix * p.Cout + co0 + c0;
+          if (!staged_out && e.out != nullptr && e.s_next != nullptr) outc = (__nv_bfloat16*)e.out + pix * p.Cout + co0 + c0;
           if (e.y_out != nullptr) yc = (__nv_bfloat16*)e.y_out + pix * p.Cout + co0 + c0;
+        }
+        if (staged_out) {
+          if (lane == 0) tma_store_wait_read();         // the previous store has finished reading this warp's staging tile
+          __syncwarp();
+          outc = stage_row;
         }
         tmem_ld_wait();
         epilogue_chunk32<EPI_ACT_RGB>(v, s_d + c0, s_b + c0, s_n + c0, s_w + c0, s_w + CO + c0, s_w + 2 * CO + c0, nz, false, rgb0, rgb1,
-                                      rgb2, outc, yc);
+                                      rgb2, outc, yc, staged_out ? stage_swz : 0);
+        if (staged_out) {   // the warp's 8 columns x 4 rows; the tensor map clips what lies outside the image
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) tma_store_4d(&tmap_o, stage_tile, co0 + c0, x0, y0 + 4 * q, b);
+        }
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[it & 1]);
@@ -814,6 +832,7 @@ conv_tc_hring_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         }
       }
     }
+    if (staged_out && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -908,8 +927,17 @@ int launch_conv_tc_hring(const void* in, const __nv_bfloat16* w, const ConvGeom&
   if (total <= 0 || total > 0x7fffffff) { set_error("conv_tc_hring: bad tile count"); return L2I_ERR_INVALID_ARG; }
   p.total_tiles = (int)total;
   constexpr int WST = 4;   // 4 x 512 MMA clocks in flight cover the L2 latency of a weight tile; three halo planes = 3 x 4608 clocks
-  constexpr int smem = kHASlots * kRPlaneStride + WST * kHN * 128 + 1024;
-  static_assert(smem + 2 * 6 * kHN * 4 + 512 <= 227 * 1024, "shared memory budget (dynamic + static epilogue vectors)");
+  constexpr int smem = kHASlots * kRPlaneStride + WST * kHN * 128 + 8 * 2048 + 1024;
+  static_assert(smem + 2 * 6 * kHN * 4 + 256 <= 227 * 1024, "shared memory budget (dynamic + static epilogue vectors)");
+  CUtensorMap to = ta;   // placeholder when the layer has no activation output / the staged path is off
+  int tma_store = 0;
+  if (g_switches.hring_store && e.out != nullptr && e.s_next != nullptr && (uintptr_t)e.out % 16 == 0) {
+    const uint64_t dims[4] = {(uint64_t)g.Cout, (uint64_t)g.out_W, (uint64_t)g.out_H, (uint64_t)g.B};
+    const uint64_t str[4] = {2, (uint64_t)g.Cout * 2, (uint64_t)g.out_W * g.Cout * 2, (uint64_t)g.out_H * g.out_W * g.Cout * 2};
+    const uint32_t box[4] = {32, 8, 4, 1};
+    L2I_TRY(make_tmap(&to, e.out, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B));
+    tma_store = 1;
+  }
   auto kern = conv_tc_hring_kernel<WST>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -917,7 +945,7 @@ int launch_conv_tc_hring(const void* in, const __nv_bfloat16* w, const ConvGeom&
     attr_set = true;
   }
   const int grid = std::min(p.total_tiles, kNumSMs);
-  kern<<<grid, 128 + 2 * 128, smem, st>>>(ta, tw, p, g.Cin / 64, tiles_n);
+  kern<<<grid, 128 + 2 * 128, smem, st>>>(ta, tw, to, p, g.Cin / 64, tiles_n, tma_store);
   return check_launch("conv_tc_hring");
 }
 
